@@ -1,0 +1,255 @@
+/*
+ * madigan_b200.h -- C ABI of the B200-native batched Madigan environment.
+ *
+ * This is the drop-in boundary for Madigan's Env.step hot path.  The reference
+ * exposes that path as the pybind11 module `env` (reference:
+ * madigan/environments/cpp/env.cpp:843-1005 binds Env; Env::step is
+ * madigan/environments/cpp/Env.h:189-256, Env::reset is Env.h:181-187).  Here the
+ * same operations act on N independent environments whose state lives in HBM as
+ * structure-of-arrays tensors owned by the caller (torch); the library is a set
+ * of stateless launchers: it allocates nothing and keeps nothing between calls
+ * except a thread-local error string.
+ *
+ * Conventions
+ *   - every pointer in MdgState / MdgStepIO / MdgDerived is a DEVICE pointer;
+ *   - per-env vectors are stored asset-major: field[a * n_envs + e]
+ *     ("[nA][N]"), so that one warp touches one contiguous 256-byte run;
+ *   - every launcher enqueues on `stream` (a cudaStream_t passed as void*) and
+ *     returns without synchronising; return value 0 = ok, <0 = MDG_E_*.
+ *   - arithmetic is IEEE fp64 without FMA contraction, sums run left to right
+ *     over the asset index (the conventions of oracle/mdg_oracle.c).
+ */
+#ifndef MADIGAN_B200_H_
+#define MADIGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDG_ABI_VERSION 3
+#define MDG_MAX_ASSETS 16
+#define MDG_GEN_NPARAM 10
+#define MDG_MAX_NSTEP 64
+
+/* error codes (reference: C++ exceptions translated by pybind11, DataTypes.h:36-46) */
+#define MDG_OK 0
+#define MDG_E_INVALID (-1)     /* bad argument / config  -> ValueError / RuntimeError */
+#define MDG_E_UNSUPPORTED (-2) /* shape outside what the kernels were built for     */
+#define MDG_E_CUDA (-3)        /* CUDA runtime error, text in mdg_last_error()      */
+
+/* RiskInfo, declaration order of DataTypes.h:70-75 */
+#define MDG_RISK_GREEN 0
+#define MDG_RISK_INSUFF_MARGIN 1
+#define MDG_RISK_MARGIN_CALL 2
+#define MDG_RISK_BLOWN_OUT 3
+
+/* synthetic generators (reference: DataSource.cpp makeDataSource :9-108) */
+enum MdgGenType {
+  MDG_GEN_SYNTH = 0,       /* DataSource.cpp:535-543  */
+  MDG_GEN_OU = 1,          /* DataSource.cpp:1173-1180 */
+  MDG_GEN_OUPAIR = 2,      /* DataSource.cpp:1232-1246 */
+  MDG_GEN_SIMPLETREND = 3, /* DataSource.cpp:1324-1359 */
+  MDG_GEN_TRENDOU = 4,     /* DataSource.cpp:1457-1502 */
+  MDG_GEN_TRENDYOU = 5,    /* DataSource.cpp:1602-1657 */
+  MDG_GEN_SAWTOOTH = 6,    /* DataSource.cpp:558-567  */
+  MDG_GEN_TRIANGLE = 7,    /* DataSource.cpp:569-578  */
+  MDG_GEN_GAUSSIAN = 8     /* DataSource.cpp:1108-1114 */
+};
+
+/* parameter slots p[] per generator type
+ *  SYNTH/SAWTOOTH/TRIANGLE: 0 freq 1 mu 2 amp 3 phase(initial x) 4 dX 5 noise
+ *  OU:          0 mean 1 theta 2 phi
+ *  OUPAIR:      0 theta 1 phi 2 noise           (same on both assets of a pair)
+ *  SIMPLETREND: 0 trendProb 1 minPeriod 2 maxPeriod 3 noise 4 start 5 dYMin 6 dYMax
+ *  TRENDOU/TRENDYOU: 0 trendProb 1 minPeriod 2 maxPeriod 3 dYMin 4 dYMax 5 start
+ *                    6 theta 7 phi 8 noiseTrend 9 emaAlpha(unused by the reference)
+ *  GAUSSIAN:    0 mean 1 var(used as stddev)
+ * generator-state rows (gstate) per asset, starting at gslot
+ *  SYNTH/SAWTOOTH/TRIANGLE: x          OU/GAUSSIAN: none
+ *  OUPAIR role 0: shared mean          OUPAIR role 1: none (uses partner's row)
+ *  SIMPLETREND: dY, flags              TRENDOU: ouMean, dY, flags
+ *  TRENDYOU: ouComponent, trendComponent, dY, flags
+ *  flags (int64 stored in the double row): bit0 trending, bit1 direction(+1),
+ *  bits 32..63 remaining trend length.
+ * noise slots: nslot = this asset's normal draw; nslot_aux = OUPair role 0 shared
+ * random-walk draw (pair order rw,x0,x1 = DataSource.cpp:1233-1235); uslot = first
+ * of 4 uniform slots (trigger, direction, length, dY) for the trend generators.
+ */
+typedef struct MdgAssetGen {
+  int32_t type;
+  int32_t role;
+  int32_t nslot;
+  int32_t nslot_aux;
+  int32_t uslot;
+  int32_t gslot;
+  int32_t partner;
+  int32_t _pad;
+  double p[MDG_GEN_NPARAM];
+} MdgAssetGen;
+
+/* per-batch constants (reference: Env.h:94-111 setters, Broker.cpp:78-85) */
+typedef struct MdgParams {
+  int32_t n_assets;
+  int32_t n_gstate;   /* rows of generator state per env            */
+  int32_t n_normals;  /* normal draws per env per tick (fixed slots) */
+  int32_t n_uniforms; /* uniform draws per env per tick              */
+  double init_cash;
+  double required_margin;
+  double maintenance_margin;
+  double slippage_rel, slippage_abs;
+  double tcost_rel, tcost_abs;
+  MdgAssetGen gen[MDG_MAX_ASSETS];
+} MdgParams;
+
+/* reward shaping (reference: utils/buffers/nstep_buffer.py:23-312,378-408 and the
+ * agent reward of modelling/algorithm/offpolicy_q.py:140-164) */
+enum MdgShaper {
+  MDG_SHAPER_OFF = 0, /* agent/shaped rewards not computed              */
+  MDG_SHAPER_SUM = 1, /* sum_default                                    */
+  MDG_SHAPER_DSR = 2,
+  MDG_SHAPER_DDR = 3,
+  MDG_SHAPER_COSINE = 4, /* cosine_port_shaper == the paper's PPC       */
+  MDG_SHAPER_SHARPE = 5,
+  MDG_SHAPER_SORTINO_A = 6,
+  MDG_SHAPER_SORTINO_B = 7
+};
+typedef struct MdgReward {
+  int32_t shaper;
+  int32_t reduce_rewards; /* agent_config.reduce_rewards: sum per-asset rewards */
+  int32_t nstep;          /* agent_config.nstep_return, 1..MDG_MAX_NSTEP        */
+  int32_t _pad;
+  double discount;
+  double adaptation_rate;
+  double cosine_temp;
+  double sortino_exp;
+  double desired_portfolio[MDG_MAX_ASSETS + 1];
+} MdgReward;
+
+/* persistent per-env state, all [rows][N] */
+typedef struct MdgState {
+  double *price;      /* [nA][N] currentPrices (== currentData for synthetic sources) */
+  double *ledger;     /* [nA][N] Portfolio::ledger_          */
+  double *mean_entry; /* [nA][N] Portfolio::meanEntryPrices_ */
+  double *borrowed;   /* [nA][N] Portfolio::borrowedMargin_  */
+  double *cash;       /* [N]     Portfolio::cash_            */
+  double *gstate;     /* [n_gstate][N] generator state       */
+  int64_t *timestamp; /* [N] generator tick counter          */
+  double *shaper_A;   /* [ra][N] DSR/DDR moving first moment  (nullable)   */
+  double *shaper_B;   /* [ra][N] DSR/DDR moving second moment (nullable)   */
+  double *nstep_ring; /* [nstep][ra][N] raw rewards waiting in the n-step buffer (nullable when nstep==1) */
+  int32_t *nstep_len; /* [N] entries currently in the n-step buffer          (nullable when nstep==1) */
+} MdgState;
+
+/* inputs and outputs of one step / reset */
+typedef struct MdgStepIO {
+  const double *units;    /* step input: (N,nA) row-major transaction units; single-asset mode: (N,) */
+  const double *normals;  /* nullable. validation mode: [ticks][n_normals][N] standard normals  */
+  const double *uniforms; /* nullable. validation mode: [ticks][n_uniforms][N] uniforms in [0,1) */
+  double *obs_price;      /* ring [k][nA][N]   State.price rows      */
+  double *obs_port;       /* ring [k][nA+1][N] State.portfolio rows (ledgerNormedFull) */
+  int64_t *obs_time;      /* ring [k][N]       State.timestamp rows  */
+  double *reward;         /* [N]  Env::step reward (log equity return, clamped) */
+  uint8_t *done;          /* [N]                                       */
+  double *trans_price;    /* [nA][N] BrokerResponse.transactionPrice   */
+  double *trans_units;    /* [nA][N] BrokerResponse.transactionUnits   */
+  double *trans_cost;     /* [nA][N] BrokerResponse.transactionCost    */
+  uint8_t *risk;          /* [nA][N] BrokerResponse.riskInfo           */
+  uint8_t *margin_call;   /* [N]     BrokerResponse.marginCall         */
+  double *agent_reward;   /* [ra][N] offpolicy_q.py:153-164 (nullable when shaper off) */
+  double *shaped_reward;  /* [nstep][ra][N] rewards popped from the n-step buffer this step (row j = j-th pop) */
+  int32_t *n_popped;      /* [N] how many rows of shaped_reward are valid this step      */
+} MdgStepIO;
+
+#define MDG_MODE_HOLD 0   /* Env::step()            Env.h:189-204 */
+#define MDG_MODE_MULTI 1  /* Env::step(units)       Env.h:206-230 */
+#define MDG_MODE_SINGLE 2 /* Env::step(idx, units)  Env.h:232-256 */
+
+typedef struct MdgLaunch {
+  int64_t n_envs;      /* envs in this slab                                   */
+  int64_t env_offset;  /* global id of env 0 (Philox counter), for sharding   */
+  uint64_t seed;       /* Philox key                                          */
+  int32_t window;      /* k, rows in the observation ring                     */
+  int32_t head;        /* ring slot that receives the newest row              */
+  int32_t mode;        /* MDG_MODE_*                                          */
+  int32_t asset_idx;   /* MDG_MODE_SINGLE only                                */
+  int32_t nstep_pos;   /* physical n-step ring slot of the entry added now    */
+  int32_t _pad;
+  void *stream;        /* cudaStream_t                                        */
+} MdgLaunch;
+
+/* derived accounting, Portfolio.cpp:140-235,243-252; any pointer may be NULL */
+typedef struct MdgDerived {
+  double *equity, *asset_value, *pnl, *balance, *available_margin, *used_margin;
+  double *borrowed_margin, *borrowed_asset_value; /* [N] each */
+  uint8_t *risk;                                   /* [N] Portfolio::checkRisk() */
+  double *position_values, *pnl_positions, *ledger_normed, *ledger_abs_normed; /* [nA][N]   */
+  double *ledger_normed_full, *ledger_abs_normed_full, *position_values_full,
+      *ledger_full;                                                             /* [nA+1][N] */
+} MdgDerived;
+
+/* window normalisers, utils/preprocessor.py:53-107 */
+enum MdgNorm {
+  MDG_NORM_NONE = 0,
+  MDG_NORM_LOOKBACK = 1,
+  MDG_NORM_LOOKBACK_LOG = 2,
+  MDG_NORM_LOG = 3,
+  MDG_NORM_STANDARD = 4,
+  MDG_NORM_LOG_STANDARD = 5,
+  MDG_NORM_EXPANDING = 6
+};
+#define MDG_DTYPE_F64 0
+#define MDG_DTYPE_F32 1
+#define MDG_LAYOUT_NKF 0 /* (N,k,F) as StackerDiscrete.current_data, preprocessor.py:183-189 */
+#define MDG_LAYOUT_NFK 1 /* (N,F,k) channels-first, what modelling/net/common.py:239-240 transposes to */
+
+/* per-slab episode statistics, see mdg_episode_stats */
+#define MDG_STATS_NSCALAR 8 /* count, sum_equity, sum_sq_equity, min_equity, max_equity, sum_reward, sum_cost, n_done */
+
+int mdg_abi_version(void);
+const char *mdg_last_error(void);
+
+/* Env::step for every env of the slab: transact -> generator tick -> reward/done ->
+ * newest observation row -> agent reward -> n-step shaped reward.
+ * Replaces Env.h:189-256 + Broker.cpp:124-178 + Portfolio.cpp:243-323 +
+ * DataSource.cpp getData family + offpolicy_q.py:140-164 + nstep_buffer.py:23-312. */
+int mdg_step(const MdgParams *params, const MdgReward *reward, const MdgState *state,
+             const MdgStepIO *io, const MdgLaunch *launch);
+
+/* Env::reset (Env.h:181-187) for the envs with mask[e]!=0 (mask==NULL: all):
+ * generator reset, fresh portfolio, one tick, and -- when fill_ticks>1 -- the
+ * fill_ticks-1 no-action ticks of StackerDiscrete.initialize_history
+ * (preprocessor.py:191-194); the rows end at ring slot launch->head.
+ * clear_nstep!=0 also empties the n-step buffer (offpolicy_q.py:94). */
+int mdg_reset(const MdgParams *params, const MdgState *state, const MdgStepIO *io,
+              const MdgLaunch *launch, const uint8_t *mask, int fill_ticks, int clear_nstep);
+
+/* Constructor state (Env.h:139-165 before the first tick): generator start values,
+ * empty ledger, cash=init_cash, timestamp=0, shaper state zero. */
+int mdg_init_state(const MdgParams *params, const MdgReward *reward, const MdgState *state,
+                   const MdgLaunch *launch);
+
+/* Portfolio's derived accounting for every env. */
+int mdg_derived(const MdgParams *params, const MdgState *state, const MdgDerived *out,
+                const MdgLaunch *launch);
+
+/* StackerDiscrete.current_data price window (preprocessor.py:183-189) with the
+ * normalisers of preprocessor.py:53-107: ring [k][F][N] -> out (N,k,F) or (N,F,k).
+ * n_valid = rows currently in the ring (<= k), oldest first. */
+int mdg_materialise_window(const double *ring, int64_t n_envs, int32_t n_feats, int32_t window,
+                           int32_t head, int32_t n_valid, int32_t norm_type, void *out,
+                           int32_t out_dtype, int32_t out_layout, void *stream);
+/* int64 timestamps ring [k][N] -> (N, n_valid) */
+int mdg_materialise_time(const int64_t *ring, int64_t n_envs, int32_t window, int32_t head,
+                         int32_t n_valid, int64_t *out, void *stream);
+
+/* Reduce the slab to MDG_STATS_NSCALAR + 2*nA doubles (per-asset sum |position value|/equity
+ * and count of non-flat positions): the vector that is all-reduced across GPUs. */
+int mdg_episode_stats(const MdgParams *params, const MdgState *state, const MdgStepIO *io,
+                      const MdgLaunch *launch, double *out /* device, zeroed by the call */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADIGAN_B200_H_ */

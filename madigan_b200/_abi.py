@@ -1,0 +1,111 @@
+"""ctypes mirror of ``include/madigan_b200.h`` (the C-ABI of the CUDA library).
+
+Field order and types must match the header byte for byte; ``tests/test_abi.py``
+checks the struct sizes against the compiled library (``mdg_sizeof``).
+"""
+import ctypes as C
+
+MDG_ABI_VERSION = 3
+MDG_MAX_ASSETS = 16
+MDG_GEN_NPARAM = 10
+MDG_MAX_NSTEP = 64
+MDG_STATS_NSCALAR = 8
+
+MDG_OK, MDG_E_INVALID, MDG_E_UNSUPPORTED, MDG_E_CUDA = 0, -1, -2, -3
+
+# RiskInfo (reference: environments/cpp/DataTypes.h:70-75)
+RISK_GREEN, RISK_INSUFF_MARGIN, RISK_MARGIN_CALL, RISK_BLOWN_OUT = 0, 1, 2, 3
+
+GEN_SYNTH, GEN_OU, GEN_OUPAIR, GEN_SIMPLETREND, GEN_TRENDOU, GEN_TRENDYOU = 0, 1, 2, 3, 4, 5
+GEN_SAWTOOTH, GEN_TRIANGLE, GEN_GAUSSIAN = 6, 7, 8
+
+SHAPER_OFF, SHAPER_SUM, SHAPER_DSR, SHAPER_DDR, SHAPER_COSINE = 0, 1, 2, 3, 4
+SHAPER_SHARPE, SHAPER_SORTINO_A, SHAPER_SORTINO_B = 5, 6, 7
+
+MODE_HOLD, MODE_MULTI, MODE_SINGLE = 0, 1, 2
+
+NORM_NONE, NORM_LOOKBACK, NORM_LOOKBACK_LOG, NORM_LOG = 0, 1, 2, 3
+NORM_STANDARD, NORM_LOG_STANDARD, NORM_EXPANDING = 4, 5, 6
+DTYPE_F64, DTYPE_F32 = 0, 1
+LAYOUT_NKF, LAYOUT_NFK = 0, 1
+
+_dp = C.c_void_p  # device (or, for the oracle, host) pointer
+
+
+class MdgAssetGen(C.Structure):
+    _fields_ = [("type", C.c_int32), ("role", C.c_int32), ("nslot", C.c_int32),
+                ("nslot_aux", C.c_int32), ("uslot", C.c_int32), ("gslot", C.c_int32),
+                ("partner", C.c_int32), ("_pad", C.c_int32),
+                ("p", C.c_double * MDG_GEN_NPARAM)]
+
+
+class MdgParams(C.Structure):
+    _fields_ = [("n_assets", C.c_int32), ("n_gstate", C.c_int32), ("n_normals", C.c_int32),
+                ("n_uniforms", C.c_int32), ("init_cash", C.c_double),
+                ("required_margin", C.c_double), ("maintenance_margin", C.c_double),
+                ("slippage_rel", C.c_double), ("slippage_abs", C.c_double),
+                ("tcost_rel", C.c_double), ("tcost_abs", C.c_double),
+                ("gen", MdgAssetGen * MDG_MAX_ASSETS)]
+
+
+class MdgReward(C.Structure):
+    _fields_ = [("shaper", C.c_int32), ("reduce_rewards", C.c_int32), ("nstep", C.c_int32),
+                ("_pad", C.c_int32), ("discount", C.c_double), ("adaptation_rate", C.c_double),
+                ("cosine_temp", C.c_double), ("sortino_exp", C.c_double),
+                ("desired_portfolio", C.c_double * (MDG_MAX_ASSETS + 1))]
+
+
+class MdgState(C.Structure):
+    _fields_ = [(n, _dp) for n in ("price", "ledger", "mean_entry", "borrowed", "cash", "gstate",
+                                   "timestamp", "shaper_A", "shaper_B", "nstep_ring", "nstep_len")]
+
+
+class MdgStepIO(C.Structure):
+    _fields_ = [(n, _dp) for n in ("units", "normals", "uniforms", "obs_price", "obs_port",
+                                   "obs_time", "reward", "done", "trans_price", "trans_units",
+                                   "trans_cost", "risk", "margin_call", "agent_reward",
+                                   "shaped_reward", "n_popped")]
+
+
+class MdgLaunch(C.Structure):
+    _fields_ = [("n_envs", C.c_int64), ("env_offset", C.c_int64), ("seed", C.c_uint64),
+                ("window", C.c_int32), ("head", C.c_int32), ("mode", C.c_int32),
+                ("asset_idx", C.c_int32), ("nstep_pos", C.c_int32), ("_pad", C.c_int32),
+                ("stream", C.c_void_p)]
+
+
+class MdgDerived(C.Structure):
+    _fields_ = [(n, _dp) for n in ("equity", "asset_value", "pnl", "balance", "available_margin",
+                                   "used_margin", "borrowed_margin", "borrowed_asset_value", "risk",
+                                   "position_values", "pnl_positions", "ledger_normed",
+                                   "ledger_abs_normed", "ledger_normed_full",
+                                   "ledger_abs_normed_full", "position_values_full", "ledger_full")]
+
+
+# every symbol include/madigan_b200.h declares: name -> (restype, argtypes)
+_P = C.POINTER
+SYMBOLS = {
+    "mdg_abi_version": (C.c_int, []),
+    "mdg_last_error": (C.c_char_p, []),
+    "mdg_step": (C.c_int, [_P(MdgParams), _P(MdgReward), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch)]),
+    "mdg_reset": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch), C.c_void_p,
+                            C.c_int, C.c_int]),
+    "mdg_init_state": (C.c_int, [_P(MdgParams), _P(MdgReward), _P(MdgState), _P(MdgLaunch)]),
+    "mdg_derived": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgDerived), _P(MdgLaunch)]),
+    "mdg_materialise_window": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p]),
+    "mdg_materialise_time": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p]),
+    "mdg_episode_stats": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch),
+                                    C.c_void_p]),
+}
+
+
+def bind(lib):
+    """Attach restype/argtypes for every declared symbol; raises AttributeError if one is missing."""
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
