@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched Env.step hot path on B200 (BASELINE.json metric).
+
+Workload (config.workload): C5 shape of SURVEY.md section 8(d) at the metric's 65,536 envs/GPU:
+16-asset portfolios = 8 independent OU pairs (theta .015, phi .01, noise .03), transaction cost
+.02 + slippage .001, required margin 1, DSR reward (adaptation .001, n-step 1, reduced), 64-step
+observation ring, synthetic actions a*unit with a in {-1,0,+1}, envs auto-reset on done.
+
+A "step" is one pass of the hot path (fused step kernel + masked auto-reset kernel) over one slab
+of 65,536 envs.  The bench rotates over `--slabs` independent slabs so that a slab's state
+(40 MB) has been evicted from the 126 MB L2 by the other slabs' traffic before it is stepped
+again: every timed step streams its state from HBM ("inputs larger than L2").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle) on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 65_536
+N_ASSETS = 16
+WINDOW = 64
+PAIRS = {f"pair{i}": {"data_source_type": "OUPair",
+                      "data_source_config": {"theta": .015, "phi": .01, "noise": .03}} for i in range(8)}
+REWARD = dict(reward_shaper_config={"reward_shaper": "DSR", "adaptation_rate": .001}, nstep_return=1,
+              discount=0.99, reduce_rewards=True)
+MARGINS = dict(required_margin=1., maintenance_margin=.25)
+COSTS = dict(transaction_cost_rel=.02, transaction_cost_abs=0., slippage_rel=.001, slippage_abs=0.)
+UNIT = 0.05 * 1_000_000. / 10.  # unit_size_proportion_avM .05 of init cash at the start price 10 (config.yaml:46)
+SEED = 0x6d616469_67616e00 ^ 5
+
+
+def bytes_per_env_step(nA=N_ASSETS, G=8, R=2, ra=1, sh=1):
+    """Algorithmic bytes per env-step, SURVEY.md 8(d) / BASELINE.md section 3."""
+    return 8 * (14 * nA + 2 * G + 2 * R + 7 + ra + sh) + nA + 2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            try:
+                sm.append(float(s[1])); mx.append(float(s[2]))
+                for n, v in zip(names, s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_env(device, env_offset, n_envs=ENVS_PER_GPU):
+    from madigan_b200.environments import Env
+    env = Env("Composite", 1_000_000., {"data_source_config": PAIRS}, n_envs=n_envs, window=WINDOW, seed=SEED,
+              device=device, env_offset=env_offset, reward=REWARD)
+    env.setRequiredMargin(MARGINS["required_margin"])
+    env.setMaintenanceMargin(MARGINS["maintenance_margin"])
+    env.setTransactionCost(COSTS["transaction_cost_rel"], COSTS["transaction_cost_abs"])
+    env.setSlippage(COSTS["slippage_rel"], COSTS["slippage_abs"])
+    env.reset(fill_history=True)
+    return env
+
+
+def synth_actions(n_batches, n_envs, generator_seed, device=None, pinned=False):
+    import torch
+    g = torch.Generator().manual_seed(generator_seed)
+    out = []
+    for _ in range(n_batches):
+        a = torch.randint(-1, 2, (n_envs, N_ASSETS), generator=g).double() * UNIT
+        if pinned:
+            a = a.pin_memory()
+        elif device is not None:
+            a = a.to(device)
+        out.append(a)
+    return out
+
+
+def cpu_baseline(sample_envs=8192, sample_steps=24, threads=None):
+    """The oracle (plain-C restatement of the reference's step loop) on the host cores: a bounded sample
+    of the same workload.  A reported baseline, not the optimisation target."""
+    import numpy as np
+    from madigan_b200.environments.data_source import make_params, make_reward
+    from oracle.oracle import OracleBatch
+    threads = threads or (os.cpu_count() or 1)
+    P, _ = make_params("Composite", PAIRS, **MARGINS, **COSTS)
+    R = make_reward(REWARD["reward_shaper_config"], 1, REWARD["discount"], True, n_assets=N_ASSETS)
+    orc = OracleBatch(sample_envs, P, R, window=WINDOW, seed=SEED, threads=threads)
+    orc.reset(fill_ticks=WINDOW)
+    rng = np.random.default_rng(0)
+    acts = [rng.integers(-1, 2, size=(sample_envs, N_ASSETS)).astype(np.float64) * UNIT for _ in range(4)]
+    for i in range(2):
+        orc.step(acts[i % 4])
+    t0 = time.perf_counter()
+    for i in range(sample_steps):
+        orc.step(acts[i % 4])
+        if orc.done.any():
+            orc.reset(mask=orc.done.copy(), fill_ticks=WINDOW)
+    dt = time.perf_counter() - t0
+    return {"value": sample_envs * sample_steps / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_envs} envs x {sample_steps} steps of the same workload (Philox noise, auto-reset), "
+                      f"oracle/mdg_oracle.c with OpenMP over envs, {dt:.2f} s"}
+
+
+def config_dict(n_gpus, slabs):
+    return {"workload": "C5 shape: 65,536 envs/GPU x 16-asset portfolios (8 OU pairs), cost .02 + slippage .001, "
+                        "DSR reward n=1, 64-step observation ring, auto-reset on done",
+            "envs_per_gpu": ENVS_PER_GPU, "n_assets": N_ASSETS, "window": WINDOW, "reward": "DSR(adaptation .001, n=1, reduced)",
+            "slabs_per_gpu": slabs, "l2": f"rotating {slabs} slabs of 65,536 envs: resident state "
+                                          f"{slabs} x 40 MB + rings exceeds the 126 MB L2, each step runs cold",
+            "bytes_per_env_step": bytes_per_env_step(), "parallelism": f"env-slab sharding x{n_gpus}, no step-path collective"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from madigan_b200 import parallel
+
+    rank, world, local = parallel.init_from_env("nccl")
+    assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    slabs, K, W = args.slabs, args.steps, args.warmup
+    per_rank = ENVS_PER_GPU * slabs
+    envs = [make_env(dev, rank * per_rank + s * ENVS_PER_GPU) for s in range(slabs)]
+    acts = synth_actions(8, ENVS_PER_GPU, 1234 + rank, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def one_step(i):
+        env = envs[i % slabs]
+        env.step(acts[i % len(acts)], auto_reset=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        one_step(i)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs ("value")
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = sum(e.launches for e in envs)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(K):
+        env = envs[(W + i) % slabs]
+        k_ev[i][0].record(stream)
+        env.step(acts[i % len(acts)])          # the fused step kernel (dominant kernel)
+        k_ev[i][1].record(stream)
+        env._reset_launch(env.t["done"], WINDOW, True, None, None)  # masked auto-reset + history fill
+    ev1.record(stream)
+    barrier()
+    launches = sum(e.launches for e in envs) - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in k_ev) / K
+    sampler.stop()
+    clocks = sampler.summary()
+
+    # ---- timed region 2: end to end through the public API with HOST buffers ("e2e")
+    host_acts = synth_actions(4, ENVS_PER_GPU, 999 + rank, pinned=True)
+    host_reward = torch.empty(ENVS_PER_GPU, dtype=torch.float64).pin_memory()
+    host_done = torch.empty(ENVS_PER_GPU, dtype=torch.bool).pin_memory()
+    for i in range(max(3, W // 2)):
+        _s, r, d, _ = envs[i % slabs].step(host_acts[i % 4], auto_reset=True)
+        host_reward.copy_(r, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        _s, r, d, _ = envs[i % slabs].step(host_acts[i % 4], auto_reset=True)   # H2D of units inside
+        host_reward.copy_(envs[i % slabs].shaped_reward[0, :, 0], non_blocking=True)  # D2H of the step's result
+        host_done.copy_(d, non_blocking=True)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d = ENVS_PER_GPU * N_ASSETS * 8
+    d2h = ENVS_PER_GPU * 8 + ENVS_PER_GPU
+
+    # ---- episode statistics: the only cross-GPU data, gathered off the step path
+    stats = envs[0].episode_stats()
+    for e in envs[1:]:
+        s2 = e.episode_stats()
+        stats[:3] += s2[:3]; stats[5:] += s2[5:]
+        stats[3] = torch.minimum(stats[3], s2[3]); stats[4] = torch.maximum(stats[4], s2[4])
+    stats = parallel.reduce_episode_stats(stats, N_ASSETS)
+
+    t = torch.tensor([ms_total, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kern_ms = (float(x) for x in t.cpu())
+    if rank == 0:
+        peak, which = peaks()
+        B = bytes_per_env_step()
+        value = world * ENVS_PER_GPU * K / (ms_total * 1e-3)
+        achieved = B * ENVS_PER_GPU / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(world, slabs),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": which, "kernel": "mdg::step_kernel<16,true>",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": B * ENVS_PER_GPU},
+            "e2e": {"value": world * ENVS_PER_GPU * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks,
+            "episode_stats": parallel.summarize_stats(stats, N_ASSETS),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as ex:  # the oracle is test infrastructure; never let it break the GPU number
+                line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  Its C++ env cannot be compiled in this image
+    (Eigen/HighFive/HDF5 absent), so this times the oracle port of it with all host threads
+    on the same config; each step is a bounded sample (8,192 envs) of the 65,536-env workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import numpy as np
+    from madigan_b200.environments.data_source import make_params, make_reward
+    from oracle.oracle import OracleBatch
+    threads = os.cpu_count() or 1
+    sample = 8192
+    P, _ = make_params("Composite", PAIRS, **MARGINS, **COSTS)
+    R = make_reward(REWARD["reward_shaper_config"], 1, REWARD["discount"], True, n_assets=N_ASSETS)
+    orc = OracleBatch(sample, P, R, window=WINDOW, seed=SEED, threads=threads)
+    orc.reset(fill_ticks=WINDOW)
+    rng = np.random.default_rng(0)
+    acts = [rng.integers(-1, 2, size=(sample, N_ASSETS)).astype(np.float64) * UNIT for _ in range(4)]
+
+    def one(i):
+        orc.step(acts[i % 4])
+        if orc.done.any():
+            orc.reset(mask=orc.done.copy(), fill_ticks=WINDOW)
+
+    for i in range(args.warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    cfg = config_dict(args.gpus, args.slabs)
+    cfg["reference_sample"] = f"each step = {sample} envs of the workload on {threads} host threads"
+    line = {"impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} envs x {args.steps} steps, oracle/mdg_oracle.c, OpenMP over envs"},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slabs", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,7 @@ typedef struct MdgReward {
   double cosine_temp;
   double sortino_exp;
   double desired_portfolio[MDG_MAX_ASSETS + 1];
+  double discounts[MDG_MAX_NSTEP]; /* math.pow(discount, i), filled by the host exactly as nstep_buffer.py:330 */
 } MdgReward;
 
 /* persistent per-env state, all [rows][N] */
@@ -208,6 +209,9 @@ enum MdgNorm {
 #define MDG_STATS_NSCALAR 8 /* count, sum_equity, sum_sq_equity, min_equity, max_equity, sum_reward, sum_cost, n_done */
 
 int mdg_abi_version(void);
+/* sizeof of the ABI structs as compiled: 0 MdgAssetGen 1 MdgParams 2 MdgReward 3 MdgState 4 MdgStepIO
+ * 5 MdgLaunch 6 MdgDerived; -1 for an unknown index (lets a binding verify its struct mirror) */
+int mdg_sizeof(int which);
 const char *mdg_last_error(void);
 
 /* Env::step for every env of the slab: transact -> generator tick -> reward/done ->

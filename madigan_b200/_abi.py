@@ -52,7 +52,8 @@ class MdgReward(C.Structure):
     _fields_ = [("shaper", C.c_int32), ("reduce_rewards", C.c_int32), ("nstep", C.c_int32),
                 ("_pad", C.c_int32), ("discount", C.c_double), ("adaptation_rate", C.c_double),
                 ("cosine_temp", C.c_double), ("sortino_exp", C.c_double),
-                ("desired_portfolio", C.c_double * (MDG_MAX_ASSETS + 1))]
+                ("desired_portfolio", C.c_double * (MDG_MAX_ASSETS + 1)),
+                ("discounts", C.c_double * MDG_MAX_NSTEP)]
 
 
 class MdgState(C.Structure):
@@ -87,6 +88,7 @@ _P = C.POINTER
 SYMBOLS = {
     "mdg_abi_version": (C.c_int, []),
     "mdg_last_error": (C.c_char_p, []),
+    "mdg_sizeof": (C.c_int, [C.c_int]),
     "mdg_step": (C.c_int, [_P(MdgParams), _P(MdgReward), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch)]),
     "mdg_reset": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch), C.c_void_p,
                             C.c_int, C.c_int]),
@@ -109,3 +111,6 @@ def bind(lib):
         fn.restype = res
         fn.argtypes = args
     return lib
+
+
+STRUCTS = (MdgAssetGen, MdgParams, MdgReward, MdgState, MdgStepIO, MdgLaunch, MdgDerived)  # mdg_sizeof order

@@ -1,0 +1,93 @@
+"""Build ``madigan_b200/libmadigan_b200.so`` in-tree with nvcc for sm_100a.
+
+``python -m madigan_b200.build`` (or ``__graft_entry__.build()``).  nvcc
+cross-compiles without a GPU; the five per-capacity instantiations of the fused
+step kernel are separate translation units so they compile in parallel.
+
+Flags that matter for parity: ``-fmad=false`` (no FMA contraction: the ledger's
+risk gates, and therefore the bit-exact positions, depend on every rounding).
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "csrc", "_obj")
+LIB = os.path.join(HERE, "libmadigan_b200.so")
+CAPS = (1, 2, 4, 8, 16)
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA library cannot be built")
+
+
+def _deps_hash(extra=""):
+    h = hashlib.sha256(extra.encode())
+    files = sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "madigan_b200.h")]
+    for f in files:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p) and p.endswith((".cu", ".cuh", ".h")):
+            h.update(open(p, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _units():
+    units = [("mdg_api.o", "mdg_api.cu", []), ("mdg_aux.o", "mdg_aux.cu", [])]
+    for cap in CAPS:
+        units.append((f"mdg_step_cap{cap}.o", "mdg_step_inst.cu", [f"-DMDG_CAP={cap}"]))
+    return units
+
+
+def build(force=False, verbose=False, ptxas_info=False):
+    """Compile if sources changed since the last build; returns the path of the .so."""
+    stamp = os.path.join(OBJ, "stamp")
+    want = _deps_hash()
+    if (not force and os.path.exists(LIB) and os.path.exists(stamp)
+            and open(stamp).read().strip() == want):
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_info else [])
+
+    def compile_one(u):
+        obj, src, defs = u
+        cmd = [nvcc] + flags + defs + ["-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return u, r
+
+    # biggest unit first so the pool's critical path is the cap-16 kernel
+    units = sorted(_units(), key=lambda u: -int(u[2][0].split("=")[1]) if u[2] else 0)
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        results = list(ex.map(compile_one, units))
+    log = []
+    for (obj, src, defs), r in results:
+        if verbose or ptxas_info:
+            log.append(f"== {obj}\n{r.stderr}")
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src} {defs}:\n{r.stdout}\n{r.stderr}")
+    objs = [os.path.join(OBJ, u[0]) for u in _units()]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(want)
+    if log:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, ptxas_info="--ptxas" in sys.argv)
+    print(path)

@@ -1,0 +1,407 @@
+// Kernels around the step path (sm_100a): Portfolio's derived accounting, the
+// StackerDiscrete window materialiser with its normalisers, and per-slab episode
+// statistics.  All HBM-bound streaming work; the window kernel stages one tile of
+// the observation ring through shared memory to turn [slot][feat][env] rows into
+// contiguous (env, k, feat) windows with coalesced traffic on both sides.
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+
+#include "mdg_common.cuh"
+
+namespace mdg {
+
+constexpr int kBlockA = 128;
+
+// ---------------------------------------------------------------------------
+// derived accounting  (Portfolio.cpp:140-235, 243-252)
+// ---------------------------------------------------------------------------
+struct DerivedArgs {
+  MdgParams P;
+  MdgState S;
+  MdgDerived D;
+  int64_t N;
+};
+
+__global__ void __launch_bounds__(kBlockA) derived_kernel(const __grid_constant__ DerivedArgs a) {
+  const int64_t N = a.N;
+  const int64_t e = (int64_t)blockIdx.x * kBlockA + threadIdx.x;
+  if (e >= N) return;
+  const int na = a.P.n_assets;
+  const MdgState& S = a.S;
+  const MdgDerived& D = a.D;
+  const double cash = S.cash[e];
+  double av, ml, bms, se, um, bav;
+  {
+    const double l = S.ledger[e], p = S.price[e], m = S.mean_entry[e];
+    const double mask = l < 0. ? 1. : 0.;
+    av = l * p; ml = m * l; bms = S.borrowed[e]; se = l * (m * mask);
+    um = fabs(l) * m; bav = l * (p * mask);
+  }
+  for (int j = 1; j < na; ++j) {
+    const double l = S.ledger[(int64_t)j * N + e], p = S.price[(int64_t)j * N + e],
+                 m = S.mean_entry[(int64_t)j * N + e];
+    const double mask = l < 0. ? 1. : 0.;
+    av = av + l * p; ml = ml + m * l; bms = bms + S.borrowed[(int64_t)j * N + e];
+    se = se + l * (m * mask); um = um + fabs(l) * m; bav = bav + l * (p * mask);
+  }
+  const double equity = cash + av - bms;  // :211-213
+  const double pnl = av - ml;             // :184-186
+  const double balance = cash + se;       // :192-197
+  if (D.equity) D.equity[e] = equity;
+  if (D.asset_value) D.asset_value[e] = av;
+  if (D.pnl) D.pnl[e] = pnl;
+  if (D.balance) D.balance[e] = balance;
+  if (D.available_margin) D.available_margin[e] = (balance + pnl) / a.P.required_margin;  // :229-231
+  if (D.used_margin) D.used_margin[e] = a.P.required_margin * um;                          // :199-201
+  if (D.borrowed_margin) D.borrowed_margin[e] = bms;
+  if (D.borrowed_asset_value) D.borrowed_asset_value[e] = bav;  // :219-223
+  if (D.risk) D.risk[e] = margin_call(cash, av, ml, bms, se, a.P.maintenance_margin) ? MDG_RISK_MARGIN_CALL : MDG_RISK_GREEN;
+  const double w0 = (cash - bms) / equity;
+  // abs-normalisers: sum |.| left to right (:144-148, :164-168)
+  double sabs = 0., sabs_full = fabs(w0);
+  for (int j = 0; j < na; ++j) {
+    const double l = S.ledger[(int64_t)j * N + e], p = S.price[(int64_t)j * N + e];
+    const double w = (l * p) / equity;
+    sabs = (j == 0) ? fabs(w) : sabs + fabs(w);
+    sabs_full = sabs_full + fabs(w);
+  }
+  if (D.ledger_normed_full) D.ledger_normed_full[e] = w0;
+  if (D.ledger_abs_normed_full) D.ledger_abs_normed_full[e] = w0 / sabs_full;
+  if (D.position_values_full) D.position_values_full[e] = cash - bms;
+  if (D.ledger_full) D.ledger_full[e] = cash - bms;
+  for (int j = 0; j < na; ++j) {
+    const double l = S.ledger[(int64_t)j * N + e], p = S.price[(int64_t)j * N + e],
+                 m = S.mean_entry[(int64_t)j * N + e];
+    const double pv = l * p;
+    const double w = pv / equity;
+    if (D.position_values) D.position_values[(int64_t)j * N + e] = pv;          // :170-172
+    if (D.pnl_positions) D.pnl_positions[(int64_t)j * N + e] = pv - m * l;      // :188-190
+    if (D.ledger_normed) D.ledger_normed[(int64_t)j * N + e] = w;               // :140-142
+    if (D.ledger_abs_normed) D.ledger_abs_normed[(int64_t)j * N + e] = w / sabs;
+    if (D.ledger_normed_full) D.ledger_normed_full[(int64_t)(j + 1) * N + e] = w;  // :150-155
+    if (D.ledger_abs_normed_full) D.ledger_abs_normed_full[(int64_t)(j + 1) * N + e] = w / sabs_full;
+    if (D.position_values_full) D.position_values_full[(int64_t)(j + 1) * N + e] = pv;  // :174-178
+    if (D.ledger_full) D.ledger_full[(int64_t)(j + 1) * N + e] = l;                      // :157-161
+  }
+}
+
+// ---------------------------------------------------------------------------
+// window materialiser  (utils/preprocessor.py:183-189 current_data, :53-107 normalisers)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double nan_to_num(double x) {  // np.nan_to_num
+  if (x != x) return 0.;
+  if (isinf(x)) return x > 0 ? DBL_MAX : -DBL_MAX;
+  return x;
+}
+
+struct WindowArgs {
+  const double* ring;  // [k][F][N]
+  void* out;
+  int64_t N;
+  int F, k, head, n_valid, norm, out_dtype, layout;
+  int envs;     // envs per block (blockDim.x)
+  int sstride;  // smem stride between rows s (doubles)
+  int estride;  // smem stride between envs   (doubles)
+};
+
+// blockDim = (envs, F): thread (x=e_local, y=f) owns one (env, feature) column.
+__global__ void window_kernel(const __grid_constant__ WindowArgs a) {
+  extern __shared__ double tile[];  // [envs][n_valid][F] with padded strides
+  const int el = threadIdx.x, f = threadIdx.y;
+  const int64_t e0 = (int64_t)blockIdx.x * a.envs;
+  const int64_t e = e0 + el;
+  const int nv = a.n_valid, F = a.F, k = a.k;
+  const bool live = e < a.N;
+  double* col = tile + (int64_t)el * a.estride + f;
+  int slot0 = (a.head - (nv - 1)) % k;
+  if (slot0 < 0) slot0 += k;
+
+  // phase 1: coalesced ring reads (consecutive envs), column into smem
+  if (live) {
+    int slot = slot0;
+    for (int s = 0; s < nv; ++s) {
+      col[s * a.sstride] = a.ring[((int64_t)slot * F + f) * a.N + e];
+      if (++slot == k) slot = 0;
+    }
+  }
+  __syncthreads();
+
+  // phase 2: normalise in place
+  if (live) {
+    switch (a.norm) {
+      case MDG_NORM_LOOKBACK: {  // x / x[-1]
+        const double last = col[(nv - 1) * a.sstride];
+        for (int s = 0; s < nv; ++s) col[s * a.sstride] = col[s * a.sstride] / last;
+        break;
+      }
+      case MDG_NORM_LOOKBACK_LOG: {  // log(x / x[-1])
+        const double last = col[(nv - 1) * a.sstride];
+        for (int s = 0; s < nv; ++s) col[s * a.sstride] = log(col[s * a.sstride] / last);
+        break;
+      }
+      case MDG_NORM_LOG:  // log(max(x, 1e-5))
+        for (int s = 0; s < nv; ++s) {
+          const double x = col[s * a.sstride];
+          col[s * a.sstride] = log((x != x) ? x : (x < 1e-5 ? 1e-5 : x));
+        }
+        break;
+      case MDG_NORM_STANDARD: {  // nan_to_num((x - mean(0)) / std(0))
+        double sum = col[0];
+        for (int s = 1; s < nv; ++s) sum = sum + col[s * a.sstride];
+        const double mean = sum / nv;
+        double ss = 0.;
+        for (int s = 0; s < nv; ++s) {
+          const double d = col[s * a.sstride] - mean;
+          ss = (s == 0) ? d * d : ss + d * d;
+        }
+        const double sd = sqrt(ss / nv);
+        for (int s = 0; s < nv; ++s) col[s * a.sstride] = nan_to_num((col[s * a.sstride] - mean) / sd);
+        break;
+      }
+      case MDG_NORM_LOG_STANDARD: {  // x = log(x); nan_to_num((x - nanmean) / nanstd)
+        double sum = 0.;
+        int cnt = 0;
+        for (int s = 0; s < nv; ++s) {
+          const double x = log(col[s * a.sstride]);
+          col[s * a.sstride] = x;
+          if (x == x) { sum = (cnt == 0) ? x : sum + x; ++cnt; }
+        }
+        const double mean = sum / cnt;
+        double ss = 0.;
+        int c2 = 0;
+        for (int s = 0; s < nv; ++s) {
+          const double x = col[s * a.sstride];
+          if (x == x) { const double d = x - mean; ss = (c2 == 0) ? d * d : ss + d * d; ++c2; }
+        }
+        const double sd = sqrt(ss / cnt);
+        for (int s = 0; s < nv; ++s) col[s * a.sstride] = nan_to_num((col[s * a.sstride] - mean) / sd);
+        break;
+      }
+      default:
+        break;
+    }
+  }
+  if (a.norm == MDG_NORM_EXPANDING) {
+    // x / _expanding_mean(x): the gufunc runs over the LAST axis (features), preprocessor.py:72-73,472-491
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int r = tid; r < a.envs * nv; r += nthr) {
+      const int re = r / nv, rs = r - re * nv;
+      if (e0 + re >= a.N) continue;
+      double* row = tile + (int64_t)re * a.estride + (int64_t)rs * a.sstride;
+      double acc = (row[0] == row[0]) ? row[0] : 0.;
+      int w = 1;
+      double prev = row[0];
+      row[0] = prev / acc;
+      for (int i = 1; i < F; ++i) {
+        const double x = row[i];
+        if (x == x) { acc = acc + x; w += 1; }
+        row[i] = x / (acc / w);
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase 3: contiguous write-out of the block's windows
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  const int per_env = nv * F;
+  const int64_t rows = (a.N - e0) < a.envs ? (a.N - e0) : a.envs;
+  const int64_t total = rows * per_env;
+  for (int64_t idx = tid; idx < total; idx += nthr) {
+    const int re = (int)(idx / per_env);
+    const int r = (int)(idx - (int64_t)re * per_env);
+    int s, ff;
+    if (a.layout == MDG_LAYOUT_NKF) { s = r / F; ff = r - s * F; } else { ff = r / nv; s = r - ff * nv; }
+    const double v = tile[(int64_t)re * a.estride + (int64_t)s * a.sstride + ff];
+    const int64_t o = e0 * per_env + idx;
+    if (a.out_dtype == MDG_DTYPE_F32) ((float*)a.out)[o] = (float)v; else ((double*)a.out)[o] = v;
+  }
+}
+
+__global__ void time_kernel(const int64_t* ring, int64_t N, int k, int head, int nv, int64_t* out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nv) return;
+  const int64_t e = idx / nv;
+  const int s = (int)(idx - e * nv);
+  int slot = (head - (nv - 1) + s) % k;
+  if (slot < 0) slot += k;
+  out[idx] = ring[(int64_t)slot * N + e];
+}
+
+// ---------------------------------------------------------------------------
+// episode statistics: one vector per slab, all-reduced across GPUs by the host (NCCL)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (!(v < __longlong_as_double((long long)assumed))) break;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+  } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (!(v > __longlong_as_double((long long)assumed))) break;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+  } while (assumed != old);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct StatsArgs {
+  MdgParams P;
+  MdgState S;
+  MdgStepIO IO;
+  int64_t N;
+  double* out;
+};
+
+__global__ void stats_init_kernel(double* out, int n) {
+  const int i = threadIdx.x;
+  if (i < n) out[i] = (i == 3) ? INFINITY : (i == 4 ? -INFINITY : 0.);
+}
+
+// grid-stride, per-thread partials -> warp shuffles -> one atomic per warp per statistic
+__global__ void __launch_bounds__(256) stats_kernel(const __grid_constant__ StatsArgs a) {
+  const int64_t N = a.N;
+  const int na = a.P.n_assets;
+  double cnt = 0., seq = 0., ssq = 0., mn = INFINITY, mx = -INFINITY, srew = 0., scost = 0., ndone = 0.;
+  double expo[MDG_MAX_ASSETS], held[MDG_MAX_ASSETS];
+#pragma unroll
+  for (int j = 0; j < MDG_MAX_ASSETS; ++j) { expo[j] = 0.; held[j] = 0.; }
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (int64_t)gridDim.x * blockDim.x) {
+    double av = 0., bms = 0.;
+    for (int j = 0; j < na; ++j) {
+      av = av + a.S.ledger[(int64_t)j * N + e] * a.S.price[(int64_t)j * N + e];
+      bms = bms + a.S.borrowed[(int64_t)j * N + e];
+    }
+    const double eq = a.S.cash[e] + av - bms;
+    cnt += 1.; seq += eq; ssq += eq * eq; mn = fmin(mn, eq); mx = fmax(mx, eq);
+    if (a.IO.reward) srew += a.IO.reward[e];
+    if (a.IO.done) ndone += a.IO.done[e] ? 1. : 0.;
+#pragma unroll
+    for (int j = 0; j < MDG_MAX_ASSETS; ++j) {
+      if (j < na) {
+        const double l = a.S.ledger[(int64_t)j * N + e];
+        if (a.IO.trans_cost) scost += a.IO.trans_cost[(int64_t)j * N + e];
+        expo[j] += fabs(l * a.S.price[(int64_t)j * N + e]) / eq;
+        held[j] += (l != 0.) ? 1. : 0.;
+      }
+    }
+  }
+  const bool lead = (threadIdx.x & 31) == 0;
+  cnt = warp_sum(cnt); seq = warp_sum(seq); ssq = warp_sum(ssq); srew = warp_sum(srew);
+  scost = warp_sum(scost); ndone = warp_sum(ndone); mn = warp_min(mn); mx = warp_max(mx);
+  if (lead) {
+    atomicAdd(&a.out[0], cnt); atomicAdd(&a.out[1], seq); atomicAdd(&a.out[2], ssq);
+    atomic_min_double(&a.out[3], mn); atomic_max_double(&a.out[4], mx);
+    atomicAdd(&a.out[5], srew); atomicAdd(&a.out[6], scost); atomicAdd(&a.out[7], ndone);
+  }
+#pragma unroll
+  for (int j = 0; j < MDG_MAX_ASSETS; ++j) {
+    if (j < na) {
+      const double x = warp_sum(expo[j]), h = warp_sum(held[j]);
+      if (lead) {
+        atomicAdd(&a.out[MDG_STATS_NSCALAR + j], x);
+        atomicAdd(&a.out[MDG_STATS_NSCALAR + na + j], h);
+      }
+    }
+  }
+}
+
+}  // namespace mdg
+
+using namespace mdg;
+
+extern "C" int mdg_derived(const MdgParams* P, const MdgState* S, const MdgDerived* D, const MdgLaunch* L) {
+  if (!P || !S || !D || !L) return set_err(MDG_E_INVALID, "null argument");
+  if (P->n_assets < 1 || P->n_assets > MDG_MAX_ASSETS) return set_err(MDG_E_UNSUPPORTED, "n_assets out of range");
+  if (L->n_envs <= 0) return L->n_envs == 0 ? MDG_OK : set_err(MDG_E_INVALID, "n_envs < 0");
+  DerivedArgs a;
+  a.P = *P; a.S = *S; a.D = *D; a.N = L->n_envs;
+  const unsigned grid = (unsigned)((a.N + kBlockA - 1) / kBlockA);
+  derived_kernel<<<grid, kBlockA, 0, (cudaStream_t)L->stream>>>(a);
+  return cuda_err(cudaGetLastError(), "mdg_derived launch");
+}
+
+extern "C" int mdg_materialise_window(const double* ring, int64_t n_envs, int32_t n_feats, int32_t window,
+                                      int32_t head, int32_t n_valid, int32_t norm_type, void* out,
+                                      int32_t out_dtype, int32_t out_layout, void* stream) {
+  if (!ring || !out) return set_err(MDG_E_INVALID, "null ring/out");
+  if (n_feats < 1 || n_feats > 64) return set_err(MDG_E_UNSUPPORTED, "n_feats must be in 1..64");
+  if (window < 1 || head < 0 || head >= window || n_valid < 1 || n_valid > window)
+    return set_err(MDG_E_INVALID, "bad window/head/n_valid");
+  if (norm_type < MDG_NORM_NONE || norm_type > MDG_NORM_EXPANDING) return set_err(MDG_E_INVALID, "bad norm_type");
+  if (out_dtype != MDG_DTYPE_F64 && out_dtype != MDG_DTYPE_F32) return set_err(MDG_E_INVALID, "bad out_dtype");
+  if (out_layout != MDG_LAYOUT_NKF && out_layout != MDG_LAYOUT_NFK) return set_err(MDG_E_INVALID, "bad layout");
+  if (n_envs <= 0) return n_envs == 0 ? MDG_OK : set_err(MDG_E_INVALID, "n_envs < 0");
+  WindowArgs a;
+  a.ring = ring; a.out = out; a.N = n_envs; a.F = n_feats; a.k = window; a.head = head; a.n_valid = n_valid;
+  a.norm = norm_type; a.out_dtype = out_dtype; a.layout = out_layout;
+  // envs per block: power of two, 8..32, about 128-256 threads, tile <= ~96 KB
+  int envs = 32;
+  while (envs > 8 && envs * n_feats > 256) envs >>= 1;
+  a.sstride = n_feats + 1;  // odd-ish row stride: conflict-free (N,F,k) reads
+  for (;;) {
+    int es = n_valid * a.sstride;
+    es += ((2 - es) % 16 + 16) % 16;  // env stride == 2 (mod 16 doubles): conflict-free column writes
+    a.estride = es;
+    if ((size_t)envs * es * sizeof(double) <= 96 * 1024 || envs == 1) break;
+    envs >>= 1;
+  }
+  a.envs = envs;
+  const size_t smem = (size_t)envs * a.estride * sizeof(double);
+  if (smem > 200 * 1024) return set_err(MDG_E_UNSUPPORTED, "window tile does not fit shared memory");
+  cudaError_t ce = cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce != cudaSuccess) return cuda_err(ce, "window smem attr");
+  const unsigned grid = (unsigned)((n_envs + envs - 1) / envs);
+  window_kernel<<<grid, dim3(envs, n_feats), smem, (cudaStream_t)stream>>>(a);
+  return cuda_err(cudaGetLastError(), "mdg_materialise_window launch");
+}
+
+extern "C" int mdg_materialise_time(const int64_t* ring, int64_t n_envs, int32_t window, int32_t head,
+                                    int32_t n_valid, int64_t* out, void* stream) {
+  if (!ring || !out) return set_err(MDG_E_INVALID, "null ring/out");
+  if (window < 1 || head < 0 || head >= window || n_valid < 1 || n_valid > window)
+    return set_err(MDG_E_INVALID, "bad window/head/n_valid");
+  if (n_envs <= 0) return n_envs == 0 ? MDG_OK : set_err(MDG_E_INVALID, "n_envs < 0");
+  const int64_t total = n_envs * n_valid;
+  time_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ring, n_envs, window, head,
+                                                                                 n_valid, out);
+  return cuda_err(cudaGetLastError(), "mdg_materialise_time launch");
+}
+
+extern "C" int mdg_episode_stats(const MdgParams* P, const MdgState* S, const MdgStepIO* IO, const MdgLaunch* L,
+                                 double* out) {
+  if (!P || !S || !L || !out) return set_err(MDG_E_INVALID, "null argument");
+  if (P->n_assets < 1 || P->n_assets > MDG_MAX_ASSETS) return set_err(MDG_E_UNSUPPORTED, "n_assets out of range");
+  StatsArgs a;
+  a.P = *P; a.S = *S;
+  if (IO) a.IO = *IO; else memset(&a.IO, 0, sizeof(a.IO));
+  a.N = L->n_envs; a.out = out;
+  cudaStream_t st = (cudaStream_t)L->stream;
+  stats_init_kernel<<<1, 64, 0, st>>>(out, MDG_STATS_NSCALAR + 2 * P->n_assets);
+  if (a.N > 0) {
+    int grid = (int)((a.N + 255) / 256);
+    if (grid > 148 * 4) grid = 148 * 4;  // a few resident CTAs per SM, grid-stride over the slab
+    stats_kernel<<<grid, 256, 0, st>>>(a);
+  }
+  return cuda_err(cudaGetLastError(), "mdg_episode_stats launch");
+}

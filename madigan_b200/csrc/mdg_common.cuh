@@ -1,0 +1,428 @@
+// Device-side building blocks of the batched Madigan environment (sm_100a).
+//
+// Everything here mirrors, per env, the arithmetic of the reference's C++ env
+// (file:line citations are relative to /root/reference/madigan/environments/cpp/).
+// The translation unit is compiled with -fmad=false: the ledger must not contract
+// a*b+c into an FMA, because branch decisions (risk gates) and therefore the
+// bit-exact ledger depend on the rounding of every intermediate.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/madigan_b200.h"
+
+#define MDG_PI2 (3.141592653589793238463 * 2)  // DataSource.h:24
+
+namespace mdg {
+
+char* err_buf();  // thread-local, 512 bytes, defined in mdg_step.cu
+
+inline int set_err(int code, const char* msg) {
+  snprintf(err_buf(), 512, "%s", msg);
+  return code;
+}
+inline int cuda_err(cudaError_t e, const char* where) {
+  if (e == cudaSuccess) return MDG_OK;
+  snprintf(err_buf(), 512, "%s: %s", where, cudaGetErrorString(e));
+  return MDG_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10, counter = (env id, stream<<16|block, tick lo, tick hi), key = seed.
+// One block -> two 64-bit words -> two draws.  Same conventions as oracle/mdg_oracle.c.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint64_t& x0, uint64_t& x1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  x0 = ((uint64_t)c1 << 32) | c0;
+  x1 = ((uint64_t)c3 << 32) | c2;
+}
+
+// Per-thread draw source: injected stream (validation mode) or Philox (free running).
+struct Draws {
+  const double* normals;   // [n_normals][N] for this tick, or nullptr
+  const double* uniforms;  // [n_uniforms][N] for this tick, or nullptr
+  int64_t N, e;
+  uint32_t gid, k0, k1, t_lo, t_hi;
+  int cached_block;  // last Box-Muller block
+  double z0, z1;
+
+  __device__ __forceinline__ void init(const MdgStepIO& io, const MdgLaunch& L, int64_t e_, int64_t tick,
+                                       int64_t tick_offset_rows_n, int64_t tick_offset_rows_u) {
+    normals = io.normals ? io.normals + tick_offset_rows_n * L.n_envs : nullptr;
+    uniforms = io.uniforms ? io.uniforms + tick_offset_rows_u * L.n_envs : nullptr;
+    N = L.n_envs;
+    e = e_;
+    gid = (uint32_t)(L.env_offset + e_);
+    k0 = (uint32_t)L.seed;
+    k1 = (uint32_t)(L.seed >> 32);
+    t_lo = (uint32_t)(uint64_t)tick;
+    t_hi = (uint32_t)((uint64_t)tick >> 32);
+    cached_block = -1;
+    z0 = z1 = 0.;
+  }
+  __device__ __forceinline__ double normal(int slot) {
+    if (normals) return normals[(int64_t)slot * N + e];
+    const int blk = slot >> 1;
+    if (blk != cached_block) {
+      uint64_t x0, x1;
+      philox4x32_10(gid, (uint32_t)blk, t_lo, t_hi, k0, k1, x0, x1);
+      const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;  // (0,1)
+      const double u2 = (double)(x1 >> 11) * 0x1.0p-53;          // [0,1)
+      const double r = sqrt(-2.0 * log(u1));
+      double s, c;
+      sincos(MDG_PI2 * u2, &s, &c);
+      z0 = r * c;
+      z1 = r * s;
+      cached_block = blk;
+    }
+    return (slot & 1) ? z1 : z0;
+  }
+  __device__ __forceinline__ double uniform(int slot) {
+    if (uniforms) return uniforms[(int64_t)slot * N + e];
+    uint64_t x0, x1;
+    philox4x32_10(gid, (1u << 16) | (uint32_t)(slot >> 1), t_lo, t_hi, k0, k1, x0, x1);
+    return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// generator state flags (bit0 trending, bit1 direction +1, bits 32.. remaining length)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double pack_flags(int trending, int dir, int len) {
+  const long long b = (long long)(trending ? 1 : 0) | (long long)(dir > 0 ? 2 : 0) |
+                      (long long)((unsigned long long)(unsigned int)len << 32);
+  return __longlong_as_double(b);
+}
+__device__ __forceinline__ void unpack_flags(double f, int& trending, int& dir, int& len) {
+  const long long b = __double_as_longlong(f);
+  trending = (int)(b & 1);
+  dir = (b & 2) ? 1 : -1;
+  len = (int)((unsigned long long)b >> 32);
+}
+__device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }  // std::max
+__device__ __forceinline__ int u_int(double u, double a, double b) { return (int)(a + floor(u * (b - a + 1.))); }
+__device__ __forceinline__ double u_real(double u, double a, double b) { return a + u * (b - a); }
+
+// One getData() of asset i (DataSource.cpp).  `price` is the asset's current price
+// (== generator value for every synthetic source), gs points at gstate row gslot for
+// this env (stride N), pair_mean carries OUPair's shared mean from role 0 to role 1.
+__device__ __forceinline__ double gen_tick(const MdgAssetGen& g, double price, double* __restrict__ gs,
+                                           int64_t N, Draws& d, double& pair_mean) {
+  const double* p = g.p;
+  switch (g.type) {
+    case MDG_GEN_SYNTH: {  // DataSource.cpp:535-543
+      const double x = gs[0];
+      price = d.normal(g.nslot) * p[5] + p[1] + p[2] * sin(MDG_PI2 * x * p[0]);
+      gs[0] = x + p[4];
+      break;
+    }
+    case MDG_GEN_SAWTOOTH: {  // :558-567
+      const double x = gs[0];
+      double ip;
+      price = d.normal(g.nslot) * p[5] + p[1] + p[2] * modf(x * p[0], &ip);
+      gs[0] = x + p[4];
+      break;
+    }
+    case MDG_GEN_TRIANGLE: {  // :569-578
+      const double x = gs[0];
+      price = d.normal(g.nslot) * p[5] + p[1] + 4 * p[2] / MDG_PI2 * asin(sin(MDG_PI2 * x / p[0]));
+      gs[0] = x + p[4];
+      break;
+    }
+    case MDG_GEN_GAUSSIAN:  // :1108-1114
+      price = d.normal(g.nslot) * p[1] + p[0];
+      break;
+    case MDG_GEN_OU:  // :1173-1180
+      price += (p[1] * (p[0] - price)) + p[0] * p[2] * d.normal(g.nslot);
+      break;
+    case MDG_GEN_OUPAIR: {  // :1232-1240
+      if (g.role == 0) {
+        double m = gs[0];
+        m += m * (d.normal(g.nslot_aux) * p[2]);
+        gs[0] = m;
+        pair_mean = m;
+      }
+      const double m = pair_mean;
+      price += (p[0] * (m - price)) + m * (d.normal(g.nslot) * p[1]);
+      break;
+    }
+    case MDG_GEN_SIMPLETREND: {  // :1324-1350
+      double y = price;
+      int trending, dir, len;
+      unpack_flags(gs[N], trending, dir, len);
+      if (trending) {
+        y += y * gs[0] * dir;
+        if (--len == 0) trending = 0;
+      } else {
+        const double r = d.uniform(g.uslot);
+        if (r < p[0]) {
+          trending = 1;
+          dir = (d.uniform(g.uslot + 1) < 0.5) ? -1 : 1;
+          len = u_int(d.uniform(g.uslot + 2), p[1], p[2]);
+          gs[0] = u_real(d.uniform(g.uslot + 3), p[5], p[6]);
+        }
+      }
+      if (y <= .1) dir = 1;
+      y += y * (d.normal(g.nslot) * p[3]);
+      y = dmax(0.01, y);
+      price = y;
+      gs[N] = pack_flags(trending, dir, len);
+      break;
+    }
+    case MDG_GEN_TRENDOU: {  // :1457-1493
+      double y = price;
+      int trending, dir, len;
+      unpack_flags(gs[2 * N], trending, dir, len);
+      if (trending) {
+        y += y * (gs[N] * dir + d.normal(g.nslot) * p[8]);
+        len -= 1;
+        if (len == 0) {
+          trending = 0;
+          gs[0] = y;
+        }
+        y = dmax(0.01, y);
+        if (y <= .1) dir = 1;
+      } else {
+        const double ou_noise = y * (d.normal(g.nslot) * p[7]);
+        const double rev = p[6] * (gs[0] - y);
+        y += rev + ou_noise;
+        const double r = d.uniform(g.uslot);
+        if (r < p[0]) {
+          trending = 1;
+          dir = (d.uniform(g.uslot + 1) < 0.5) ? -1 : 1;
+          len = u_int(d.uniform(g.uslot + 2), p[1], p[2]);
+          gs[N] = u_real(d.uniform(g.uslot + 3), p[3], p[4]);
+        }
+      }
+      price = y;
+      gs[2 * N] = pack_flags(trending, dir, len);
+      break;
+    }
+    case MDG_GEN_TRENDYOU: {  // :1602-1642
+      int trending, dir, len;
+      unpack_flags(gs[3 * N], trending, dir, len);
+      double ou = gs[0], tr = gs[N];
+      const double ou_noise = tr * (d.normal(g.nslot) * p[7]);
+      const double rev = p[6] * (-ou);
+      ou += rev + ou_noise;
+      if (trending) {
+        tr += tr * (gs[2 * N] * dir);
+        tr = dmax(0.1, tr);
+        if (tr <= .1) {
+          dir = 1;
+          trending = 1;
+          len = u_int(d.uniform(g.uslot + 2), p[1], p[2]);
+        }
+        if (--len == 0) trending = 0;
+      } else {
+        const double r = d.uniform(g.uslot);
+        if (r < p[0]) {
+          trending = 1;
+          dir = (d.uniform(g.uslot + 1) < 0.5) ? -1 : 1;
+          len = u_int(d.uniform(g.uslot + 2), p[1], p[2]);
+          gs[2 * N] = u_real(d.uniform(g.uslot + 3), p[3], p[4]);
+        }
+      }
+      gs[0] = ou;
+      gs[N] = tr;
+      price = ou + tr;
+      gs[3 * N] = pack_flags(trending, dir, len);
+      break;
+    }
+  }
+  return price;
+}
+
+// DataSource::reset() of asset i; returns the new price (Synth/OU/Gaussian: unchanged).
+__device__ __forceinline__ double gen_reset(const MdgAssetGen& g, double price, double* __restrict__ gs,
+                                            int64_t N) {
+  switch (g.type) {
+    case MDG_GEN_OUPAIR:  // DataSource.cpp:1242-1246
+      if (g.role == 0) gs[0] = 10.;
+      return 10.;
+    case MDG_GEN_SIMPLETREND:  // :1352-1359
+      gs[N] = pack_flags(0, 1, 0);
+      return g.p[4];
+    case MDG_GEN_TRENDOU: {  // :1495-1502 (direction, dY untouched)
+      int trending, dir, len;
+      unpack_flags(gs[2 * N], trending, dir, len);
+      gs[0] = g.p[5];
+      gs[2 * N] = pack_flags(0, dir, 0);
+      return g.p[5];
+    }
+    case MDG_GEN_TRENDYOU: {  // :1644-1657
+      int trending, dir, len;
+      unpack_flags(gs[3 * N], trending, dir, len);
+      gs[0] = 0.;
+      gs[N] = g.p[5];
+      gs[3 * N] = pack_flags(0, dir, 0);
+      return g.p[5];
+    }
+    default:
+      return price;
+  }
+}
+
+// constructor state of asset i (initParams of each source); returns the start price
+__device__ __forceinline__ double gen_start(const MdgAssetGen& g, double* __restrict__ gs, int64_t N) {
+  switch (g.type) {
+    case MDG_GEN_SYNTH:
+    case MDG_GEN_SAWTOOTH:
+    case MDG_GEN_TRIANGLE:
+      gs[0] = g.p[3];  // DataSource.cpp:463
+      return 0.;
+    case MDG_GEN_OU:
+    case MDG_GEN_GAUSSIAN:
+      return g.p[0];  // :1129, :1066
+    case MDG_GEN_OUPAIR:
+      if (g.role == 0) gs[0] = 10.;  // :1194
+      return 10.;                    // :1192
+    case MDG_GEN_SIMPLETREND:
+      gs[0] = 0.;
+      gs[N] = pack_flags(0, 1, 0);
+      return g.p[4];  // :1273
+    case MDG_GEN_TRENDOU:
+      gs[0] = g.p[5];
+      gs[N] = 0.;
+      gs[2 * N] = pack_flags(0, 1, 0);
+      return g.p[5];
+    case MDG_GEN_TRENDYOU:
+      gs[0] = 0.;
+      gs[N] = g.p[5];
+      gs[2 * N] = 0.;
+      gs[3 * N] = pack_flags(0, 1, 0);
+      return g.p[5];
+  }
+  return 0.;
+}
+
+// ---------------------------------------------------------------------------
+// Portfolio in registers.  CAP = compile-time capacity, na = live assets (== CAP when EXACT).
+// ---------------------------------------------------------------------------
+template <int CAP>
+struct Port {
+  double price[CAP], led[CAP], mep[CAP], bm[CAP];
+  double cash;
+};
+
+// The four left-to-right folds every accounting quantity is made of
+// (Portfolio.cpp:180-182 assetValue, :185 meanEntry.ledger, :207-209 borrowedMargin, :192-196 short entry value)
+template <int CAP, bool EXACT>
+__device__ __forceinline__ void port_sums(const Port<CAP>& q, int na, double& av, double& ml, double& bms,
+                                          double& se) {
+  av = q.led[0] * q.price[0];
+  ml = q.mep[0] * q.led[0];
+  bms = q.bm[0];
+  se = q.led[0] * (q.mep[0] * (q.led[0] < 0. ? 1. : 0.));
+#pragma unroll
+  for (int j = 1; j < CAP; ++j) {
+    if (EXACT || j < na) {
+      av = av + q.led[j] * q.price[j];
+      ml = ml + q.mep[j] * q.led[j];
+      bms = bms + q.bm[j];
+      se = se + q.led[j] * (q.mep[j] * (q.led[j] < 0. ? 1. : 0.));
+    }
+  }
+}
+
+// Portfolio::checkRisk() :243-252 from the folds
+__device__ __forceinline__ bool margin_call(double cash, double av, double ml, double bms, double se,
+                                            double maintM) {
+  const double pnl = av - ml;
+  const double marginRequired = maintM * pnl;
+  const double equity = cash + av - bms;
+  if (equity <= -marginRequired) return true;
+  const double balance = cash + se;
+  if ((balance + pnl) <= -marginRequired) return true;
+  return false;
+}
+
+// Broker::handleTransaction(port, i, units) Broker.cpp:124-142 with Portfolio::checkRisk(i,units)
+// :254-279 and Portfolio::handleTransaction :284-323 for asset I.
+// I must be a compile-time constant after unrolling (the portfolio lives in registers).
+template <int CAP, bool EXACT>
+__device__ __forceinline__ int broker_transaction(Port<CAP>& q, int na, const MdgParams& P, const int I,
+                                                  double units, double& tp, double& tu, double& tc) {
+  tp = 0.;
+  tu = 0.;
+  tc = 0.;
+  if (!(units != 0.)) return MDG_RISK_GREEN;
+  const double price = q.price[I];
+  double cur = q.led[I];
+  // ---- Portfolio::checkRisk(i, units)
+  int risk = MDG_RISK_GREEN;
+  const bool opposite = (signbit(units) != 0) != (signbit(cur) != 0);
+  if (!opposite || units > -1 * cur) {
+    double av, ml, bms, se;
+    port_sums<CAP, EXACT>(q, na, av, ml, bms, se);
+    const double pnl = av - ml;
+    const double balance = q.cash + se;
+    const double availableMargin = (balance + pnl) / P.required_margin;
+    if (opposite) {
+      const double excess = units + cur;
+      if (availableMargin <= fabs(price * excess) || balance <= 0.) risk = MDG_RISK_INSUFF_MARGIN;
+    } else {
+      if (margin_call(q.cash, av, ml, bms, se, P.maintenance_margin)) {
+        risk = MDG_RISK_MARGIN_CALL;
+      } else {
+        const double cashAmount = price * units;
+        if (availableMargin <= fabs(cashAmount) || balance <= 0.) risk = MDG_RISK_INSUFF_MARGIN;
+      }
+    }
+  }
+  if (risk != MDG_RISK_GREEN) return risk;
+  // ---- Broker::applySlippage / getTransactionCost  Broker.cpp:171-178
+  const double slippage = (price * P.slippage_rel) + P.slippage_abs;
+  const double transactionPrice = units < 0 ? (price - slippage) : (price + slippage);
+  const double transactionCost = fabs(units * price) * P.tcost_rel + P.tcost_abs;
+  tp = transactionPrice;
+  tu = units;
+  tc = transactionCost;
+  // ---- Portfolio::handleTransaction  Portfolio.cpp:284-323
+  double mep = q.mep[I];
+  if (opposite) {
+    if (fabs(units) > fabs(cur)) {
+      units += cur;
+      q.cash += cur * transactionPrice;
+      cur = 0.;
+      mep = transactionPrice;
+    }
+  } else {
+    mep += (transactionPrice - mep) * (units / (units + cur));
+  }
+  const double amount = transactionPrice * units;
+  const double marginToUse = amount * P.required_margin;
+  const double marginToBorrow = amount - marginToUse;
+  double bm = q.bm[I];
+  bm += marginToBorrow;
+  q.cash -= (marginToUse + transactionCost);
+  cur += units;
+  if (fabs(cur) < 0.000001) {
+    mep = 0.;
+    if (bm > 0.) {
+      q.cash -= bm;
+      bm = 0.;
+    }
+  }
+  if (bm < 0.) {
+    q.cash -= bm;
+    bm = 0.;
+  }
+  q.led[I] = cur;
+  q.mep[I] = mep;
+  q.bm[I] = bm;
+  return MDG_RISK_GREEN;
+}
+
+}  // namespace mdg

@@ -11,7 +11,7 @@ Deviations, all listed in SURVEY.md Appendix A:
     (A11; the reference keys them by type name in an unordered_map).
   * ``SimpleTrend`` takes config keys, never positions (A10).
 """
-from collections import OrderedDict
+import math
 
 from .. import _abi as A
 
@@ -197,6 +197,10 @@ def make_reward(reward_shaper_config=None, nstep_return=1, discount=0.99, reduce
     R.nstep = max(1, int(nstep_return))
     R.discount = float(discount)
     R.reduce_rewards = int(bool(reduce_rewards))
+    if R.nstep > A.MDG_MAX_NSTEP:
+        raise ValueError(f"nstep_return {R.nstep} > MDG_MAX_NSTEP={A.MDG_MAX_NSTEP}")
+    for i in range(R.nstep):  # NStepBuffer.__init__, nstep_buffer.py:330
+        R.discounts[i] = math.pow(R.discount, i)
     if not enabled:
         R.shaper = A.SHAPER_OFF
         return R

@@ -1,0 +1,467 @@
+"""Batched drop-in for Madigan's C++ ``Env`` (reference: madigan/environments/cpp/Env.h:17-256,
+bound to Python in madigan/environments/cpp/env.cpp:843-1005).
+
+Same member names as the reference; every scalar becomes an ``(N,)`` CUDA tensor, every
+per-asset vector an ``(N,nA)`` tensor.  torch owns all state (structure-of-arrays,
+``[rows][N]`` storage, fp64); every operation is one launch of a hand-written sm_100a
+kernel through the C-ABI in ``include/madigan_b200.h``.  There is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _abi as A
+from .._lib import check, lib
+from ..utils.data import BrokerResponse, EnvInfo, State
+from .data_source import make_params, make_reward
+
+
+def _cfg_get(cfg, key, default=None):
+    if cfg is None:
+        return default
+    try:
+        if key in cfg:
+            v = cfg[key]
+            return default if v is None else v
+    except TypeError:
+        pass
+    return getattr(cfg, key, default)
+
+
+class Asset:
+    """reference: environments/cpp/Assets.h:10-30."""
+
+    def __init__(self, code):
+        self.code = code
+        self.name = code
+
+    def __repr__(self):
+        return f"Asset({self.code})"
+
+    def __eq__(self, other):
+        return getattr(other, "code", other) == self.code
+
+
+class _View:
+    """`env.portfolio` / `env.account` / `env.broker` / `env.dataSource`: the reference returns the
+    C++ sub-objects (Env.h:51-55); with one account and one portfolio per env they all read the same
+    ledger, so they are views of the env."""
+
+    def __init__(self, env):
+        self._env = env
+
+    def __getattr__(self, name):
+        return getattr(self._env, name)
+
+    def currentData(self):
+        return self._env.currentData
+
+    def checkRisk(self, *a):
+        return self._env.checkRisk(*a)
+
+
+class Env:
+    def __init__(self, dataSourceType, initCash=1_000_000., config=None, *, n_envs=None, device=None,
+                 window=None, seed=None, env_offset=0, reward=None):
+        """``Env(data_source_type, init_cash, config)`` as the reference (env.cpp:843-849); the batched
+        keys ``n_envs``, ``seed``, ``device``, ``window_length`` may come from ``config`` or keywords.
+        ``reward``: None (env reward only) or a dict with ``reward_shaper_config``, ``nstep_return``,
+        ``discount``, ``reduce_rewards`` to also compute the agent + shaped rewards in the step kernel."""
+        self._lib = lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("madigan_b200.Env needs a CUDA device (sm_100a); there is no CPU fallback")
+        ds_cfg = _cfg_get(config, "data_source_config")
+        self.N = int(n_envs if n_envs is not None else _cfg_get(config, "n_envs", 1))
+        self.device = torch.device(device if device is not None else _cfg_get(config, "device", "cuda"))
+        if self.device.type != "cuda":
+            raise RuntimeError("madigan_b200.Env runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        pre = _cfg_get(config, "preprocessor_config")
+        self.k = int(window if window is not None else _cfg_get(pre, "window_length", 64))
+        self.seed = int(seed if seed is not None else _cfg_get(config, "seed", 0x6d61646967616e00))
+        self.env_offset = int(env_offset)
+        self._dataSourceType = dataSourceType
+        self._initCash = float(initCash)
+        self.P, self._asset_names = make_params(dataSourceType, ds_cfg, init_cash=initCash)
+        self.nA = self.P.n_assets
+        if reward is None and _cfg_get(config, "reward_shaper_config") is not None and _cfg_get(config, "in_kernel_rewards", False):
+            ac = _cfg_get(config, "agent_config")
+            reward = dict(reward_shaper_config=_cfg_get(config, "reward_shaper_config"),
+                          nstep_return=_cfg_get(ac, "nstep_return", 1), discount=_cfg_get(ac, "discount", 0.99),
+                          reduce_rewards=_cfg_get(ac, "reduce_rewards", False))
+        if reward is None:
+            self.R = make_reward(enabled=False)
+        else:
+            self.R = make_reward(reward.get("reward_shaper_config"), reward.get("nstep_return", 1),
+                                 reward.get("discount", 0.99), reward.get("reduce_rewards", False),
+                                 n_assets=self.nA)
+        self.ra = 1 if self.R.reduce_rewards else self.nA
+        self._alloc()
+        self.head = 0
+        self.n_valid = 0
+        self._gstep = 0
+        self._version = 0
+        self._derived_version = -1
+        self.launches = 0  # kernels launched so far (bench.py's gpu_launches)
+        with torch.cuda.device(self.device):
+            check(self._lib.mdg_init_state(C.byref(self.P), C.byref(self.R), C.byref(self._S), C.byref(self._launch())))
+            self.launches += 1
+            # the constructor consumes one generator tick (Env.h:160)
+            self._reset_launch(None, 1, False, None, None)
+        self.n_valid = 1
+
+    # ------------------------------------------------------------------ allocation
+    def _alloc(self):
+        N, nA, k, dev = self.N, self.nA, self.k, self.device
+        f8 = dict(dtype=torch.float64, device=dev)
+        z = torch.zeros
+        self.t = dict(
+            price=z((nA, N), **f8), ledger=z((nA, N), **f8), mean_entry=z((nA, N), **f8),
+            borrowed=z((nA, N), **f8), cash=z((N,), **f8), gstate=z((max(1, self.P.n_gstate), N), **f8),
+            timestamp=z((N,), dtype=torch.int64, device=dev),
+            shaper_A=z((self.ra, N), **f8), shaper_B=z((self.ra, N), **f8),
+            nstep_ring=z((self.R.nstep, self.ra, N), **f8), nstep_len=z((N,), dtype=torch.int32, device=dev),
+            obs_price=z((k, nA, N), **f8), obs_port=z((k, nA + 1, N), **f8),
+            obs_time=z((k, N), dtype=torch.int64, device=dev),
+            reward=z((N,), **f8), done=z((N,), dtype=torch.bool, device=dev),
+            trans_price=z((nA, N), **f8), trans_units=z((nA, N), **f8), trans_cost=z((nA, N), **f8),
+            risk=z((nA, N), dtype=torch.uint8, device=dev), margin_call=z((N,), dtype=torch.bool, device=dev),
+            agent_reward=z((self.ra, N), **f8), shaped_reward=z((self.R.nstep, self.ra, N), **f8),
+            n_popped=z((N,), dtype=torch.int32, device=dev),
+            units=z((N, nA), **f8),
+        )
+        S = A.MdgState()
+        for name in ("price", "ledger", "mean_entry", "borrowed", "cash", "gstate", "timestamp", "shaper_A",
+                     "shaper_B", "nstep_ring", "nstep_len"):
+            setattr(S, name, self.t[name].data_ptr())
+        self._S = S
+        IO = A.MdgStepIO()
+        for name in ("obs_price", "obs_port", "obs_time", "reward", "done", "trans_price", "trans_units",
+                     "trans_cost", "risk", "margin_call", "agent_reward", "shaped_reward", "n_popped"):
+            setattr(IO, name, self.t[name].data_ptr())
+        self._IO = IO
+        self._d = None
+
+    def _launch(self, mode=A.MODE_HOLD, asset_idx=0):
+        return A.MdgLaunch(n_envs=self.N, env_offset=self.env_offset, seed=self.seed, window=self.k,
+                           head=self.head, mode=mode, asset_idx=asset_idx,
+                           nstep_pos=self._gstep % self.R.nstep,
+                           stream=torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _noise(self, normals, uniforms):
+        keep = []
+        ptrs = []
+        for x in (normals, uniforms):
+            if x is None:
+                ptrs.append(None)
+                continue
+            x = torch.as_tensor(x, dtype=torch.float64).to(self.device).contiguous()
+            keep.append(x)
+            ptrs.append(x.data_ptr())
+        return ptrs[0], ptrs[1], keep
+
+    # ------------------------------------------------------------------ setters (Env.h:94-111)
+    def setRequiredMargin(self, reqM):
+        self.P.required_margin = float(reqM)
+        self._version += 1
+
+    def setMaintenanceMargin(self, mainM):
+        self.P.maintenance_margin = float(mainM)
+        self._version += 1
+
+    def setSlippage(self, slippagePct=0., slippageAbs=0.):
+        self.P.slippage_rel, self.P.slippage_abs = float(slippagePct), float(slippageAbs)
+
+    def setTransactionCost(self, transactionPct=0., transactionAbs=0.):
+        self.P.tcost_rel, self.P.tcost_abs = float(transactionPct), float(transactionAbs)
+
+    # ------------------------------------------------------------------ reset / step
+    def _reset_launch(self, mask, fill_ticks, clear_nstep, normals, uniforms):
+        io = self._IO
+        n_ptr, u_ptr, keep = self._noise(normals, uniforms)
+        io.normals, io.uniforms, io.units = n_ptr, u_ptr, None
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask)
+            if m.dtype == torch.bool:
+                m = m.view(torch.uint8)  # same bytes, no conversion kernel
+            m = m.to(device=self.device, dtype=torch.uint8).contiguous()
+            if tuple(m.shape) != (self.N,):
+                raise ValueError(f"mask must have shape ({self.N},)")
+        check(self._lib.mdg_reset(C.byref(self.P), C.byref(self._S), C.byref(io), C.byref(self._launch()),
+                                  None if m is None else m.data_ptr(), int(fill_ticks), int(clear_nstep)))
+        self.launches += 1
+        self._version += 1
+        del keep
+
+    def _state(self):
+        t = self.t
+        return State(t["obs_price"][self.head].t(), t["obs_port"][self.head].t(), t["obs_time"][self.head],
+                     _ring=(self, self._version))
+
+    def reset(self, mask=None, fill_history=False, normals=None, uniforms=None):
+        """Env::reset (Env.h:181-187).  ``mask``: (N,) bool/uint8, only those envs (None = all).
+        ``fill_history``: also run the k-1 no-action ticks of ``initialize_history``
+        (reference: utils/preprocessor.py:191-194) so the whole window belongs to the new episode.
+        Returns the newest State row."""
+        fill = self.k if fill_history else 1
+        with torch.cuda.device(self.device):
+            self._reset_launch(mask, fill, True, normals, uniforms)
+        if mask is None:
+            self.n_valid = fill
+        return self._state()
+
+    def step(self, *args, normals=None, uniforms=None, auto_reset=False):
+        """``step()`` hold (Env.h:189-204); ``step(units)`` with units (N,nA) (Env.h:206-230);
+        ``step(assetIdx|assetCode, units)`` with units (N,) (Env.h:232-256, env.cpp:995-1005).
+        Returns ``(State, reward (N,), done (N,) bool, EnvInfo)``; the tensors are views of live
+        buffers that the next call overwrites (same aliasing as the reference's Eigen maps)."""
+        asset_idx = 0
+        if len(args) == 0:
+            mode, units = A.MODE_HOLD, None
+        elif len(args) == 1:
+            mode, units = A.MODE_MULTI, args[0]
+        elif len(args) == 2:
+            mode, units = A.MODE_SINGLE, args[1]
+            a = args[0]
+            asset_idx = self._asset_names.index(a) if isinstance(a, str) else int(a)
+            if not 0 <= asset_idx < self.nA:
+                raise IndexError("asset index out of range")
+        else:
+            raise TypeError("step() takes at most (assetIdx, units)")
+        io = self._IO
+        with torch.cuda.device(self.device):
+            if units is not None:
+                u = torch.as_tensor(units, dtype=torch.float64)
+                want = (self.N, self.nA) if mode == A.MODE_MULTI else (self.N,)
+                if self.N == 1 and u.dim() == len(want) - 1:
+                    u = u.unsqueeze(0)
+                if tuple(u.shape) != want:
+                    raise ValueError(f"units must have shape {want}, got {tuple(u.shape)}")
+                if u.device != self.device or not u.is_contiguous():
+                    dst = self.t["units"] if mode == A.MODE_MULTI else self.t["units"].view(-1)[:self.N]
+                    dst.copy_(u, non_blocking=True)  # H2D from (pinned) host memory, async on this stream
+                    u = dst
+                io.units = u.data_ptr()
+            else:
+                io.units = None
+            n_ptr, u_ptr, keep = self._noise(normals, uniforms)
+            io.normals, io.uniforms = n_ptr, u_ptr
+            self.head = (self.head + 1) % self.k
+            self.n_valid = min(self.k, self.n_valid + 1)
+            L = self._launch(mode, asset_idx)
+            check(self._lib.mdg_step(C.byref(self.P), C.byref(self.R), C.byref(self._S), C.byref(io), C.byref(L)))
+            self.launches += 1
+            if mode != A.MODE_HOLD and self.R.shaper != A.SHAPER_OFF:
+                self._gstep += 1
+            self._version += 1
+            if auto_reset:
+                self._reset_launch(self.t["done"], self.k, True, None, None)
+        t = self.t
+        resp = BrokerResponse("", t["obs_time"][self.head], t["trans_price"].t(), t["trans_units"].t(),
+                              t["trans_cost"].t(), t["risk"].t(), t["margin_call"])
+        return self._state(), t["reward"], t["done"], EnvInfo(resp, False)
+
+    # ------------------------------------------------------------------ in-kernel rewards
+    @property
+    def agent_reward(self):
+        """(N, ra) per-asset (or reduced) log-return reward of the last step (offpolicy_q.py:152-164)."""
+        return self.t["agent_reward"].t()
+
+    @property
+    def shaped_reward(self):
+        """(nstep, N, ra): rewards popped from the n-step buffer by the last step, row j = j-th pop;
+        ``n_popped`` (N,) says how many rows are valid (nstep_buffer.py:342-361, replay_buffer.py:68-80)."""
+        return self.t["shaped_reward"].transpose(1, 2)
+
+    @property
+    def n_popped(self):
+        return self.t["n_popped"]
+
+    def reset_shaper_state(self):
+        """Zero the DSR/DDR moments (they persist across episode resets in the reference, A18)."""
+        self.t["shaper_A"].zero_()
+        self.t["shaper_B"].zero_()
+
+    # ------------------------------------------------------------------ derived accounting
+    def _derived(self):
+        if self._derived_version == self._version and self._d is not None:
+            return self._d
+        N, nA, dev = self.N, self.nA, self.device
+        if self._d is None:
+            f8 = dict(dtype=torch.float64, device=dev)
+            d = {n: torch.empty((N,), **f8) for n in ("equity", "asset_value", "pnl", "balance", "available_margin",
+                                                      "used_margin", "borrowed_margin", "borrowed_asset_value")}
+            d["risk"] = torch.empty((N,), dtype=torch.uint8, device=dev)
+            for n in ("position_values", "pnl_positions", "ledger_normed", "ledger_abs_normed"):
+                d[n] = torch.empty((nA, N), **f8)
+            for n in ("ledger_normed_full", "ledger_abs_normed_full", "position_values_full", "ledger_full"):
+                d[n] = torch.empty((nA + 1, N), **f8)
+            self._d = d
+            D = A.MdgDerived()
+            for n, v in d.items():
+                setattr(D, n, v.data_ptr())
+            self._D = D
+        with torch.cuda.device(self.device):
+            check(self._lib.mdg_derived(C.byref(self.P), C.byref(self._S), C.byref(self._D), C.byref(self._launch())))
+        self.launches += 1
+        self._derived_version = self._version
+        return self._d
+
+    def invalidate(self):
+        """Call after writing into a live state view (e.g. ``env.currentPrices[:, 1] = 4``)."""
+        self._version += 1
+
+    # live views of state (reference: return_value_policy::reference, env.cpp:897-913)
+    @property
+    def currentPrices(self): return self.t["price"].t()
+    @property
+    def currentData(self): return self.t["price"].t()
+    @property
+    def ledger(self): return self.t["ledger"].t()
+    @property
+    def meanEntryPrices(self): return self.t["mean_entry"].t()
+    @property
+    def borrowedMarginLedger(self): return self.t["borrowed"].t()
+    @property
+    def cash(self): return self.t["cash"]
+    @property
+    def timestamp(self): return self.t["timestamp"]
+    @property
+    def currentTime(self): return self.t["timestamp"]
+    # derived (Portfolio.cpp:140-235)
+    @property
+    def equity(self): return self._derived()["equity"]
+    @property
+    def assetValue(self): return self._derived()["asset_value"]
+    @property
+    def pnl(self): return self._derived()["pnl"]
+    @property
+    def balance(self): return self._derived()["balance"]
+    @property
+    def availableMargin(self): return self._derived()["available_margin"]
+    @property
+    def usedMargin(self): return self._derived()["used_margin"]
+    @property
+    def borrowedMargin(self): return self._derived()["borrowed_margin"]
+    @property
+    def borrowedAssetValue(self): return self._derived()["borrowed_asset_value"]
+    @property
+    def positionValues(self): return self._derived()["position_values"].t()
+    @property
+    def positionValuesFull(self): return self._derived()["position_values_full"].t()
+    @property
+    def pnlPositions(self): return self._derived()["pnl_positions"].t()
+    @property
+    def ledgerFull(self): return self._derived()["ledger_full"].t()
+    @property
+    def ledgerNormed(self): return self._derived()["ledger_normed"].t()
+    @property
+    def ledgerNormedFull(self): return self._derived()["ledger_normed_full"].t()
+    @property
+    def ledgerAbsNormed(self): return self._derived()["ledger_abs_normed"].t()
+    @property
+    def ledgerAbsNormedFull(self): return self._derived()["ledger_abs_normed_full"].t()
+
+    def checkRisk(self):
+        """Portfolio::checkRisk() per env -> (N,) uint8 RiskInfo (Portfolio.cpp:243-252)."""
+        return self._derived()["risk"]
+
+    def dataEnd(self):
+        return False  # synthetic sources never end (DataSource.h)
+
+    # static info
+    @property
+    def nAssets(self): return self.nA
+    @property
+    def nFeats(self): return self.nA  # nFeats()==nAssets() for every synthetic source (DataSource.h:231)
+    @property
+    def n_envs(self): return self.N
+    @property
+    def assets(self): return [Asset(n) for n in self._asset_names]
+    @property
+    def isDateTime(self): return False
+    @property
+    def initCash(self): return self._initCash
+    @property
+    def requiredMargin(self): return self.P.required_margin
+    @property
+    def maintenanceMargin(self): return self.P.maintenance_margin
+    @property
+    def dataSourceType(self): return self._dataSourceType
+    @property
+    def dataSource(self): return _View(self)
+    @property
+    def portfolio(self): return _View(self)
+    @property
+    def account(self): return _View(self)
+    @property
+    def broker(self): return _View(self)
+
+    # ------------------------------------------------------------------ window / stats / checkpoint
+    def window(self, norm_type=None, dtype=torch.float64, channels_first=False, n_valid=None, out=None):
+        """Materialise the price window ``(N, n_valid, nF)`` (or ``(N, nF, n_valid)``) from the observation
+        ring, normalised as ``make_normalizer(norm_type)`` (reference: utils/preprocessor.py:53-107,183-189)."""
+        from ..utils.preprocessor import NORM_TYPES
+        nv = self.n_valid if n_valid is None else int(n_valid)
+        norm = NORM_TYPES[norm_type]
+        shape = (self.N, self.nA, nv) if channels_first else (self.N, nv, self.nA)
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=self.device)
+        dt = A.DTYPE_F32 if out.dtype == torch.float32 else A.DTYPE_F64
+        with torch.cuda.device(self.device):
+            check(self._lib.mdg_materialise_window(self.t["obs_price"].data_ptr(), self.N, self.nA, self.k, self.head,
+                                                   nv, norm, out.data_ptr(), dt,
+                                                   A.LAYOUT_NFK if channels_first else A.LAYOUT_NKF,
+                                                   torch.cuda.current_stream(self.device).cuda_stream))
+        self.launches += 1
+        return out
+
+    def portfolio_window(self, n_valid=None):
+        """(N, n_valid, nA+1) window of ledgerNormedFull rows, oldest first."""
+        nv = self.n_valid if n_valid is None else int(n_valid)
+        out = torch.empty((self.N, nv, self.nA + 1), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.mdg_materialise_window(self.t["obs_port"].data_ptr(), self.N, self.nA + 1, self.k,
+                                                   self.head, nv, A.NORM_NONE, out.data_ptr(), A.DTYPE_F64,
+                                                   A.LAYOUT_NKF, torch.cuda.current_stream(self.device).cuda_stream))
+        self.launches += 1
+        return out
+
+    def time_window(self, n_valid=None):
+        nv = self.n_valid if n_valid is None else int(n_valid)
+        out = torch.empty((self.N, nv), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.mdg_materialise_time(self.t["obs_time"].data_ptr(), self.N, self.k, self.head, nv,
+                                                 out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+        self.launches += 1
+        return out
+
+    def episode_stats(self):
+        """Per-slab statistics vector (device, fp64): [count, sum_equity, sum_sq_equity, min_equity,
+        max_equity, sum_reward, sum_cost, n_done, exposure[nA], held[nA]] -- the only data that ever
+        crosses GPUs (all-reduced by ``madigan_b200.parallel``)."""
+        out = torch.empty((A.MDG_STATS_NSCALAR + 2 * self.nA,), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.mdg_episode_stats(C.byref(self.P), C.byref(self._S), C.byref(self._IO),
+                                              C.byref(self._launch()), out.data_ptr()))
+        self.launches += 2
+        return out
+
+    def state_dict(self):
+        """Checkpoint of the env (the reference cannot checkpoint its env: wall-clock seeded RNG)."""
+        sd = {k_: v.clone() for k_, v in self.t.items() if k_ != "units"}
+        sd["_meta"] = dict(head=self.head, n_valid=self.n_valid, gstep=self._gstep, seed=self.seed,
+                           env_offset=self.env_offset)
+        return sd
+
+    def load_state_dict(self, sd):
+        for k_, v in sd.items():
+            if k_ == "_meta":
+                continue
+            self.t[k_].copy_(v)
+        m = sd["_meta"]
+        self.head, self.n_valid, self._gstep = m["head"], m["n_valid"], m["gstep"]
+        self.seed, self.env_offset = m["seed"], m["env_offset"]
+        self._version += 1

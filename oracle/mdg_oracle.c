@@ -477,8 +477,7 @@ static double ddr_value(double A, double B, double r) { /* :146-156 */
 static double shaper_pop_value(OrcEnv *e, int c) {
   const MdgReward *R = &e->R;
   int n = e->ring_len;
-  double disc[MDG_MAX_NSTEP];
-  for (int j = 0; j < n; ++j) disc[j] = pow(R->discount, (double)j); /* :330 */
+  const double *disc = R->discounts; /* [math.pow(discount, i)], :330, computed by the host */
   switch (R->shaper) {
     case MDG_SHAPER_SUM:
     case MDG_SHAPER_COSINE: { /* :23-27, :182-204 (cosine term already folded in at add time) */
