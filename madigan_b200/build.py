@@ -31,14 +31,22 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the CUDA library cannot be built")
 
 
-def _deps_hash(extra=""):
-    h = hashlib.sha256(extra.encode())
-    files = sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "madigan_b200.h")]
+def _extra_flags():
+    """MDG_EXTRA_NVCC_FLAGS lets a profiling run try a variant (e.g. -DMDG_MINB16=2) without editing sources."""
+    return os.environ.get("MDG_EXTRA_NVCC_FLAGS", "").split()
+
+
+def _deps_hash(src="", defs=()):
+    """Hash of everything one object depends on: its source, every header, and the flags."""
+    h = hashlib.sha256()
+    files = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h")) or f == src]
+    files.append(os.path.join("..", "..", "include", "madigan_b200.h"))
     for f in files:
         p = os.path.join(CSRC, f)
-        if os.path.isfile(p) and p.endswith((".cu", ".cuh", ".h")):
+        if os.path.isfile(p):
+            h.update(f.encode())
             h.update(open(p, "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + list(defs) + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -51,23 +59,31 @@ def _units():
 
 def build(force=False, verbose=False, ptxas_info=False):
     """Compile if sources changed since the last build; returns the path of the .so."""
-    stamp = os.path.join(OBJ, "stamp")
-    want = _deps_hash()
-    if (not force and os.path.exists(LIB) and os.path.exists(stamp)
-            and open(stamp).read().strip() == want):
+    os.makedirs(OBJ, exist_ok=True)
+    flags = list(NVCC_FLAGS) + _extra_flags() + (["-Xptxas", "-v"] if ptxas_info else [])
+
+    def stale(u):
+        obj, src, defs = u
+        st = os.path.join(OBJ, obj + ".hash")
+        return (force or ptxas_info or not os.path.exists(os.path.join(OBJ, obj)) or not os.path.exists(st)
+                or open(st).read().strip() != _deps_hash(src, defs))
+
+    todo = [u for u in _units() if stale(u)]
+    if not todo and os.path.exists(LIB):
         return LIB
     nvcc = _nvcc()
-    os.makedirs(OBJ, exist_ok=True)
-    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_info else [])
 
     def compile_one(u):
         obj, src, defs = u
         cmd = [nvcc] + flags + defs + ["-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode == 0:
+            with open(os.path.join(OBJ, obj + ".hash"), "w") as f:
+                f.write(_deps_hash(src, defs))
         return u, r
 
     # biggest unit first so the pool's critical path is the cap-16 kernel
-    units = sorted(_units(), key=lambda u: -int(u[2][0].split("=")[1]) if u[2] else 0)
+    units = sorted(todo, key=lambda u: -int(u[2][0].split("=")[1]) if u[2] else 0)
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         results = list(ex.map(compile_one, units))
     log = []
@@ -81,8 +97,6 @@ def build(force=False, verbose=False, ptxas_info=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
-        f.write(want)
     if log:
         print("\n".join(log))
     return LIB

@@ -22,6 +22,7 @@ struct ResetArgs {
 };
 
 __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ ResetArgs a) {
+  __shared__ double s_z[kMaxNormals][kBlock];
   const MdgParams& P = a.P;
   const int64_t N = a.L.n_envs;
   const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -42,19 +43,23 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ R
   const double cash = P.init_cash;
   a.S.cash[e] = cash;
   int64_t ts = a.S.timestamp[e];
+  double* zcol = &s_z[0][threadIdx.x];
+#pragma unroll 1
   for (int t = 0; t < a.fill_ticks; ++t) {
-    Draws d;
-    d.init(a.IO, a.L, e, ts, (int64_t)t * P.n_normals, (int64_t)t * P.n_uniforms);
+    GenCtx ctx;
+    ctx_init(ctx, zcol, kBlock, a.IO.uniforms ? a.IO.uniforms + (int64_t)t * P.n_uniforms * N : nullptr, a.L, e, ts);
+    fill_normals(zcol, kBlock, P.n_normals, a.IO.normals ? a.IO.normals + (int64_t)t * P.n_normals * N : nullptr, ctx);
     double pair_mean = 0.;
     int slot = (a.L.head - (a.fill_ticks - 1 - t)) % k;
     if (slot < 0) slot += k;
     // flat portfolio: equity == cash, ledgerNormedFull == [cash/equity, 0*price/equity ...]
     const double eq = cash + 0. - 0.;
     a.IO.obs_port[((int64_t)slot * (na + 1)) * N + e] = (cash - 0.) / eq;
+#pragma unroll 1
     for (int i = 0; i < na; ++i) {
       const MdgAssetGen& g = P.gen[i];
       double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-      const double pr = gen_tick(g, a.S.price[(int64_t)i * N + e], gs, N, d, pair_mean);
+      const double pr = gen_tick(g, a.S.price[(int64_t)i * N + e], gs, ctx, pair_mean);
       a.S.price[(int64_t)i * N + e] = pr;
       a.IO.obs_price[((int64_t)slot * na + i) * N + e] = pr;
       a.IO.obs_port[((int64_t)slot * (na + 1) + i + 1) * N + e] = (0. * pr) / eq;

@@ -48,53 +48,64 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   x1 = ((uint64_t)c3 << 32) | c2;
 }
 
-// Per-thread draw source: injected stream (validation mode) or Philox (free running).
-struct Draws {
-  const double* normals;   // [n_normals][N] for this tick, or nullptr
-  const double* uniforms;  // [n_uniforms][N] for this tick, or nullptr
+// Draw conventions (shared with oracle/mdg_oracle.c): normal slot s lives in Philox block s>>1 of
+// stream 0 (Box-Muller: lane 0 = r*cos, lane 1 = r*sin), uniform slot s in block s>>1 of stream 1.
+constexpr int kMaxNormals = (3 * MDG_MAX_ASSETS) / 2;  // 3 per OU pair, 1 per other asset
+
+struct GenCtx {
+  const double* z;         // this env's normals for this tick: z[slot * zstride] (shared memory column)
+  int zstride;
+  const double* uniforms;  // [n_uniforms][N] for this tick (validation mode) or nullptr
   int64_t N, e;
   uint32_t gid, k0, k1, t_lo, t_hi;
-  int cached_block;  // last Box-Muller block
-  double z0, z1;
-
-  __device__ __forceinline__ void init(const MdgStepIO& io, const MdgLaunch& L, int64_t e_, int64_t tick,
-                                       int64_t tick_offset_rows_n, int64_t tick_offset_rows_u) {
-    normals = io.normals ? io.normals + tick_offset_rows_n * L.n_envs : nullptr;
-    uniforms = io.uniforms ? io.uniforms + tick_offset_rows_u * L.n_envs : nullptr;
-    N = L.n_envs;
-    e = e_;
-    gid = (uint32_t)(L.env_offset + e_);
-    k0 = (uint32_t)L.seed;
-    k1 = (uint32_t)(L.seed >> 32);
-    t_lo = (uint32_t)(uint64_t)tick;
-    t_hi = (uint32_t)((uint64_t)tick >> 32);
-    cached_block = -1;
-    z0 = z1 = 0.;
-  }
-  __device__ __forceinline__ double normal(int slot) {
-    if (normals) return normals[(int64_t)slot * N + e];
-    const int blk = slot >> 1;
-    if (blk != cached_block) {
-      uint64_t x0, x1;
-      philox4x32_10(gid, (uint32_t)blk, t_lo, t_hi, k0, k1, x0, x1);
-      const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;  // (0,1)
-      const double u2 = (double)(x1 >> 11) * 0x1.0p-53;          // [0,1)
-      const double r = sqrt(-2.0 * log(u1));
-      double s, c;
-      sincos(MDG_PI2 * u2, &s, &c);
-      z0 = r * c;
-      z1 = r * s;
-      cached_block = blk;
-    }
-    return (slot & 1) ? z1 : z0;
-  }
-  __device__ __forceinline__ double uniform(int slot) {
-    if (uniforms) return uniforms[(int64_t)slot * N + e];
-    uint64_t x0, x1;
-    philox4x32_10(gid, (1u << 16) | (uint32_t)(slot >> 1), t_lo, t_hi, k0, k1, x0, x1);
-    return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
-  }
 };
+
+__device__ __forceinline__ void ctx_init(GenCtx& c, const double* z, int zstride, const double* uniforms,
+                                         const MdgLaunch& L, int64_t e, int64_t tick) {
+  c.z = z;
+  c.zstride = zstride;
+  c.uniforms = uniforms;
+  c.N = L.n_envs;
+  c.e = e;
+  c.gid = (uint32_t)(L.env_offset + e);
+  c.k0 = (uint32_t)L.seed;
+  c.k1 = (uint32_t)(L.seed >> 32);
+  c.t_lo = (uint32_t)(uint64_t)tick;
+  c.t_hi = (uint32_t)((uint64_t)tick >> 32);
+}
+
+// All normal draws of one env for one tick into a shared-memory column.  A ROLLED loop over
+// Philox blocks: one copy of Philox + Box-Muller in the instruction stream (the first version
+// inlined it at every draw site and the kernel became I-cache bound, profiles/r1_notes.md).
+__device__ __forceinline__ void fill_normals(double* zcol, int zstride, int n_normals, const double* normals,
+                                             const GenCtx& c) {
+  if (normals) {  // validation mode: injected stream [n_normals][N]
+    for (int s = 0; s < n_normals; ++s) zcol[s * zstride] = normals[(int64_t)s * c.N + c.e];
+    return;
+  }
+  const int nb = (n_normals + 1) >> 1;
+#pragma unroll 2
+  for (int b = 0; b < nb; ++b) {
+    uint64_t x0, x1;
+    philox4x32_10(c.gid, (uint32_t)b, c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
+    const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;  // (0,1)
+    const double u2 = (double)(x1 >> 11) * 0x1.0p-53;          // [0,1)
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincos(MDG_PI2 * u2, &sn, &cs);
+    zcol[(2 * b) * zstride] = r * cs;
+    if (2 * b + 1 < n_normals) zcol[(2 * b + 1) * zstride] = r * sn;
+  }
+}
+
+__device__ __forceinline__ double draw_normal(const GenCtx& c, int slot) { return c.z[slot * c.zstride]; }
+
+static __device__ __noinline__ double draw_uniform(const GenCtx& c, int slot) {
+  if (c.uniforms) return c.uniforms[(int64_t)slot * c.N + c.e];
+  uint64_t x0, x1;
+  philox4x32_10(c.gid, (1u << 16) | (uint32_t)(slot >> 1), c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
+  return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
+}
 
 // ---------------------------------------------------------------------------
 // generator state flags (bit0 trending, bit1 direction +1, bits 32.. remaining length)
@@ -117,44 +128,46 @@ __device__ __forceinline__ double u_real(double u, double a, double b) { return 
 // One getData() of asset i (DataSource.cpp).  `price` is the asset's current price
 // (== generator value for every synthetic source), gs points at gstate row gslot for
 // this env (stride N), pair_mean carries OUPair's shared mean from role 0 to role 1.
-__device__ __forceinline__ double gen_tick(const MdgAssetGen& g, double price, double* __restrict__ gs,
-                                           int64_t N, Draws& d, double& pair_mean) {
+// NOT inlined: one copy of the nine generator bodies per kernel (generic / Composite path).
+static __device__ __noinline__ double gen_tick(const MdgAssetGen& g, double price, double* __restrict__ gs,
+                                               const GenCtx& d, double& pair_mean) {
   const double* p = g.p;
+  const int64_t N = d.N;
   switch (g.type) {
     case MDG_GEN_SYNTH: {  // DataSource.cpp:535-543
       const double x = gs[0];
-      price = d.normal(g.nslot) * p[5] + p[1] + p[2] * sin(MDG_PI2 * x * p[0]);
+      price = draw_normal(d, g.nslot) * p[5] + p[1] + p[2] * sin(MDG_PI2 * x * p[0]);
       gs[0] = x + p[4];
       break;
     }
     case MDG_GEN_SAWTOOTH: {  // :558-567
       const double x = gs[0];
       double ip;
-      price = d.normal(g.nslot) * p[5] + p[1] + p[2] * modf(x * p[0], &ip);
+      price = draw_normal(d, g.nslot) * p[5] + p[1] + p[2] * modf(x * p[0], &ip);
       gs[0] = x + p[4];
       break;
     }
     case MDG_GEN_TRIANGLE: {  // :569-578
       const double x = gs[0];
-      price = d.normal(g.nslot) * p[5] + p[1] + 4 * p[2] / MDG_PI2 * asin(sin(MDG_PI2 * x / p[0]));
+      price = draw_normal(d, g.nslot) * p[5] + p[1] + 4 * p[2] / MDG_PI2 * asin(sin(MDG_PI2 * x / p[0]));
       gs[0] = x + p[4];
       break;
     }
     case MDG_GEN_GAUSSIAN:  // :1108-1114
-      price = d.normal(g.nslot) * p[1] + p[0];
+      price = draw_normal(d, g.nslot) * p[1] + p[0];
       break;
     case MDG_GEN_OU:  // :1173-1180
-      price += (p[1] * (p[0] - price)) + p[0] * p[2] * d.normal(g.nslot);
+      price += (p[1] * (p[0] - price)) + p[0] * p[2] * draw_normal(d, g.nslot);
       break;
     case MDG_GEN_OUPAIR: {  // :1232-1240
       if (g.role == 0) {
         double m = gs[0];
-        m += m * (d.normal(g.nslot_aux) * p[2]);
+        m += m * (draw_normal(d, g.nslot_aux) * p[2]);
         gs[0] = m;
         pair_mean = m;
       }
       const double m = pair_mean;
-      price += (p[0] * (m - price)) + m * (d.normal(g.nslot) * p[1]);
+      price += (p[0] * (m - price)) + m * (draw_normal(d, g.nslot) * p[1]);
       break;
     }
     case MDG_GEN_SIMPLETREND: {  // :1324-1350
@@ -165,16 +178,16 @@ __device__ __forceinline__ double gen_tick(const MdgAssetGen& g, double price, d
         y += y * gs[0] * dir;
         if (--len == 0) trending = 0;
       } else {
-        const double r = d.uniform(g.uslot);
+        const double r = draw_uniform(d, g.uslot);
         if (r < p[0]) {
           trending = 1;
-          dir = (d.uniform(g.uslot + 1) < 0.5) ? -1 : 1;
-          len = u_int(d.uniform(g.uslot + 2), p[1], p[2]);
-          gs[0] = u_real(d.uniform(g.uslot + 3), p[5], p[6]);
+          dir = (draw_uniform(d, g.uslot + 1) < 0.5) ? -1 : 1;
+          len = u_int(draw_uniform(d, g.uslot + 2), p[1], p[2]);
+          gs[0] = u_real(draw_uniform(d, g.uslot + 3), p[5], p[6]);
         }
       }
       if (y <= .1) dir = 1;
-      y += y * (d.normal(g.nslot) * p[3]);
+      y += y * (draw_normal(d, g.nslot) * p[3]);
       y = dmax(0.01, y);
       price = y;
       gs[N] = pack_flags(trending, dir, len);
@@ -185,7 +198,7 @@ __device__ __forceinline__ double gen_tick(const MdgAssetGen& g, double price, d
       int trending, dir, len;
       unpack_flags(gs[2 * N], trending, dir, len);
       if (trending) {
-        y += y * (gs[N] * dir + d.normal(g.nslot) * p[8]);
+        y += y * (gs[N] * dir + draw_normal(d, g.nslot) * p[8]);
         len -= 1;
         if (len == 0) {
           trending = 0;
@@ -194,15 +207,15 @@ __device__ __forceinline__ double gen_tick(const MdgAssetGen& g, double price, d
         y = dmax(0.01, y);
         if (y <= .1) dir = 1;
       } else {
-        const double ou_noise = y * (d.normal(g.nslot) * p[7]);
+        const double ou_noise = y * (draw_normal(d, g.nslot) * p[7]);
         const double rev = p[6] * (gs[0] - y);
         y += rev + ou_noise;
-        const double r = d.uniform(g.uslot);
+        const double r = draw_uniform(d, g.uslot);
         if (r < p[0]) {
           trending = 1;
-          dir = (d.uniform(g.uslot + 1) < 0.5) ? -1 : 1;
-          len = u_int(d.uniform(g.uslot + 2), p[1], p[2]);
-          gs[N] = u_real(d.uniform(g.uslot + 3), p[3], p[4]);
+          dir = (draw_uniform(d, g.uslot + 1) < 0.5) ? -1 : 1;
+          len = u_int(draw_uniform(d, g.uslot + 2), p[1], p[2]);
+          gs[N] = u_real(draw_uniform(d, g.uslot + 3), p[3], p[4]);
         }
       }
       price = y;
@@ -213,7 +226,7 @@ __device__ __forceinline__ double gen_tick(const MdgAssetGen& g, double price, d
       int trending, dir, len;
       unpack_flags(gs[3 * N], trending, dir, len);
       double ou = gs[0], tr = gs[N];
-      const double ou_noise = tr * (d.normal(g.nslot) * p[7]);
+      const double ou_noise = tr * (draw_normal(d, g.nslot) * p[7]);
       const double rev = p[6] * (-ou);
       ou += rev + ou_noise;
       if (trending) {
@@ -222,16 +235,16 @@ __device__ __forceinline__ double gen_tick(const MdgAssetGen& g, double price, d
         if (tr <= .1) {
           dir = 1;
           trending = 1;
-          len = u_int(d.uniform(g.uslot + 2), p[1], p[2]);
+          len = u_int(draw_uniform(d, g.uslot + 2), p[1], p[2]);
         }
         if (--len == 0) trending = 0;
       } else {
-        const double r = d.uniform(g.uslot);
+        const double r = draw_uniform(d, g.uslot);
         if (r < p[0]) {
           trending = 1;
-          dir = (d.uniform(g.uslot + 1) < 0.5) ? -1 : 1;
-          len = u_int(d.uniform(g.uslot + 2), p[1], p[2]);
-          gs[2 * N] = u_real(d.uniform(g.uslot + 3), p[3], p[4]);
+          dir = (draw_uniform(d, g.uslot + 1) < 0.5) ? -1 : 1;
+          len = u_int(draw_uniform(d, g.uslot + 2), p[1], p[2]);
+          gs[2 * N] = u_real(draw_uniform(d, g.uslot + 3), p[3], p[4]);
         }
       }
       gs[0] = ou;
