@@ -21,53 +21,107 @@ struct ResetArgs {
   int clear_nstep;
 };
 
-__global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ ResetArgs a) {
-  __shared__ double s_z[kMaxNormals][kBlock];
+// Envs that reset are rare and scattered, and each must fast-forward fill_ticks generator ticks
+// (A17: a reset consumes k ticks).  One thread per env would leave 31 lanes idle for 64 ticks in
+// almost every warp, so the block (a) compacts the indices of its resetting envs in shared memory
+// and (b) spreads (generator group, env) items over ALL its threads: an OU pair or a single
+// asset is an independent stochastic process, and Philox draws are addressed by (env, tick, slot),
+// so any lane can compute any group's path.
+constexpr int kResetBlock = 256;
+
+__global__ void __launch_bounds__(kResetBlock) reset_kernel(const __grid_constant__ ResetArgs a) {
+  __shared__ int s_list[kResetBlock];
+  __shared__ long long s_ts[kResetBlock];
+  __shared__ int s_leader[MDG_MAX_ASSETS];
+  __shared__ int s_count, s_nlead;
   const MdgParams& P = a.P;
   const int64_t N = a.L.n_envs;
-  const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (e >= N) return;
-  if (a.mask && !a.mask[e]) return;
+  const int tid = threadIdx.x;
+  const int64_t e0 = (int64_t)blockIdx.x * kResetBlock;
   const int na = P.n_assets;
   const int k = a.L.window;
-  if (a.clear_nstep && a.S.nstep_len) a.S.nstep_len[e] = 0;  // offpolicy_q.py:94
-  // dataSource_->reset(); fresh Broker/Account/Portfolio (Env.h:150-165)
-  for (int i = 0; i < na; ++i) {
-    const MdgAssetGen& g = P.gen[i];
-    double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-    a.S.price[(int64_t)i * N + e] = gen_reset(g, a.S.price[(int64_t)i * N + e], gs, N);
-    a.S.ledger[(int64_t)i * N + e] = 0.;
-    a.S.mean_entry[(int64_t)i * N + e] = 0.;
-    a.S.borrowed[(int64_t)i * N + e] = 0.;
+  const int fill = a.fill_ticks;
+  if (tid == 0) {
+    s_count = 0;
+    int n = 0;
+    for (int i = 0; i < na; ++i)
+      if (!(P.gen[i].type == MDG_GEN_OUPAIR && P.gen[i].role == 1)) s_leader[n++] = i;
+    s_nlead = n;
   }
+  __syncthreads();
+  {  // (a) warp-aggregated compaction of the resetting envs of this block
+    const int64_t e = e0 + tid;
+    const bool flag = (e < N) && (!a.mask || a.mask[e]);
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+    int base = 0;
+    if ((tid & 31) == 0 && ballot) base = atomicAdd(&s_count, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (flag) s_list[base + __popc(ballot & ((1u << (tid & 31)) - 1u))] = tid;
+  }
+  __syncthreads();
+  const int nd = s_count;
+  if (nd == 0) return;
   const double cash = P.init_cash;
-  a.S.cash[e] = cash;
-  int64_t ts = a.S.timestamp[e];
-  double* zcol = &s_z[0][threadIdx.x];
-#pragma unroll 1
-  for (int t = 0; t < a.fill_ticks; ++t) {
-    GenCtx ctx;
-    ctx_init(ctx, zcol, kBlock, a.IO.uniforms ? a.IO.uniforms + (int64_t)t * P.n_uniforms * N : nullptr, a.L, e, ts);
-    fill_normals(zcol, kBlock, P.n_normals, a.IO.normals ? a.IO.normals + (int64_t)t * P.n_normals * N : nullptr, ctx);
-    double pair_mean = 0.;
-    int slot = (a.L.head - (a.fill_ticks - 1 - t)) % k;
-    if (slot < 0) slot += k;
-    // flat portfolio: equity == cash, ledgerNormedFull == [cash/equity, 0*price/equity ...]
-    const double eq = cash + 0. - 0.;
-    a.IO.obs_port[((int64_t)slot * (na + 1)) * N + e] = (cash - 0.) / eq;
-#pragma unroll 1
-    for (int i = 0; i < na; ++i) {
-      const MdgAssetGen& g = P.gen[i];
-      double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-      const double pr = gen_tick(g, a.S.price[(int64_t)i * N + e], gs, ctx, pair_mean);
-      a.S.price[(int64_t)i * N + e] = pr;
-      a.IO.obs_price[((int64_t)slot * na + i) * N + e] = pr;
-      a.IO.obs_port[((int64_t)slot * (na + 1) + i + 1) * N + e] = (0. * pr) / eq;
+  const double eq = cash + 0. - 0.;  // flat portfolio: equity == cash
+  // per-env scalars: fresh Broker/Account/Portfolio (Env.h:150-165), cash weight and timestamps of the rows
+  for (int it = tid; it < nd; it += kResetBlock) {
+    const int64_t e = e0 + s_list[it];
+    if (a.clear_nstep && a.S.nstep_len) a.S.nstep_len[e] = 0;  // offpolicy_q.py:94
+    a.S.cash[e] = cash;
+    const long long ts = a.S.timestamp[e];
+    s_ts[it] = ts;
+    a.S.timestamp[e] = ts + fill;
+    for (int t = 0; t < fill; ++t) {
+      int slot = (a.L.head - (fill - 1 - t)) % k;
+      if (slot < 0) slot += k;
+      a.IO.obs_port[((int64_t)slot * (na + 1)) * N + e] = (cash - 0.) / eq;
+      a.IO.obs_time[(int64_t)slot * N + e] = ts + t + 1;
     }
-    ts += 1;
-    a.IO.obs_time[(int64_t)slot * N + e] = ts;
   }
-  a.S.timestamp[e] = ts;
+  __syncthreads();
+  // (b) items ordered leader-major so that neighbouring lanes run the same generator type
+  const int nitems = nd * s_nlead;
+  for (int item = tid; item < nitems; item += kResetBlock) {
+    const int l = item / nd, d = item - l * nd;
+    const int64_t e = e0 + s_list[d];
+    const int i0 = s_leader[l];
+    const int cnt = (P.gen[i0].type == MDG_GEN_OUPAIR) ? 2 : 1;
+    double pr[2];
+    for (int c = 0; c < cnt; ++c) {  // dataSource_->reset() and the empty ledger
+      const MdgAssetGen& g = P.gen[i0 + c];
+      double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
+      pr[c] = gen_reset(g, a.S.price[(int64_t)(i0 + c) * N + e], gs, N);
+      a.S.ledger[(int64_t)(i0 + c) * N + e] = 0.;
+      a.S.mean_entry[(int64_t)(i0 + c) * N + e] = 0.;
+      a.S.borrowed[(int64_t)(i0 + c) * N + e] = 0.;
+    }
+    LazyDraws dr;
+    dr.N = N; dr.e = e;
+    dr.gid = (uint32_t)(a.L.env_offset + e);
+    dr.k0 = (uint32_t)a.L.seed; dr.k1 = (uint32_t)(a.L.seed >> 32);
+    const long long ts0 = s_ts[d];
+#pragma unroll 1
+    for (int t = 0; t < fill; ++t) {
+      const long long tick = ts0 + t;
+      dr.t_lo = (uint32_t)(unsigned long long)tick;
+      dr.t_hi = (uint32_t)((unsigned long long)tick >> 32);
+      dr.cached_block = -1;
+      dr.normals = a.IO.normals ? a.IO.normals + (int64_t)t * P.n_normals * N : nullptr;
+      dr.uniforms = a.IO.uniforms ? a.IO.uniforms + (int64_t)t * P.n_uniforms * N : nullptr;
+      int slot = (a.L.head - (fill - 1 - t)) % k;
+      if (slot < 0) slot += k;
+      double pair_mean = 0.;
+#pragma unroll 1
+      for (int c = 0; c < cnt; ++c) {
+        const MdgAssetGen& g = P.gen[i0 + c];
+        double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
+        pr[c] = gen_tick(g, pr[c], gs, dr, pair_mean);
+        a.IO.obs_price[((int64_t)slot * na + i0 + c) * N + e] = pr[c];
+        a.IO.obs_port[((int64_t)slot * (na + 1) + i0 + c + 1) * N + e] = (0. * pr[c]) / eq;
+      }
+    }
+    for (int c = 0; c < cnt; ++c) a.S.price[(int64_t)(i0 + c) * N + e] = pr[c];
+  }
 }
 
 // constructor state (Env.h:139-165 before the first tick)
@@ -160,8 +214,8 @@ extern "C" int mdg_reset(const MdgParams* P, const MdgState* S, const MdgStepIO*
   ResetArgs a;
   a.P = *P; a.S = *S; a.IO = *IO; a.L = *L;
   a.mask = mask; a.fill_ticks = fill_ticks; a.clear_nstep = clear_nstep;
-  const unsigned grid = (unsigned)((L->n_envs + kBlock - 1) / kBlock);
-  reset_kernel<<<grid, kBlock, 0, (cudaStream_t)L->stream>>>(a);
+  const unsigned grid = (unsigned)((L->n_envs + kResetBlock - 1) / kResetBlock);
+  reset_kernel<<<grid, kResetBlock, 0, (cudaStream_t)L->stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_reset launch");
 }
 

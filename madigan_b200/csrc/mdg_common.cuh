@@ -107,6 +107,40 @@ static __device__ __noinline__ double draw_uniform(const GenCtx& c, int slot) {
   return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
 }
 
+// Draw source of the reset kernel: normals computed on demand (one Box-Muller block cached), so that
+// different lanes can fast-forward different generator groups of different envs.
+struct LazyDraws {
+  const double* normals;   // [n_normals][N] for this tick (validation mode) or nullptr
+  const double* uniforms;  // [n_uniforms][N] for this tick (validation mode) or nullptr
+  int64_t N, e;
+  uint32_t gid, k0, k1, t_lo, t_hi;
+  int cached_block;
+  double z0, z1;
+};
+static __device__ __noinline__ double draw_normal(LazyDraws& c, int slot) {
+  if (c.normals) return c.normals[(int64_t)slot * c.N + c.e];
+  const int blk = slot >> 1;
+  if (blk != c.cached_block) {
+    uint64_t x0, x1;
+    philox4x32_10(c.gid, (uint32_t)blk, c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
+    const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
+    const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincos(MDG_PI2 * u2, &sn, &cs);
+    c.z0 = r * cs;
+    c.z1 = r * sn;
+    c.cached_block = blk;
+  }
+  return (slot & 1) ? c.z1 : c.z0;
+}
+static __device__ __noinline__ double draw_uniform(LazyDraws& c, int slot) {
+  if (c.uniforms) return c.uniforms[(int64_t)slot * c.N + c.e];
+  uint64_t x0, x1;
+  philox4x32_10(c.gid, (1u << 16) | (uint32_t)(slot >> 1), c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
+  return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
+}
+
 // ---------------------------------------------------------------------------
 // generator state flags (bit0 trending, bit1 direction +1, bits 32.. remaining length)
 // ---------------------------------------------------------------------------
@@ -128,9 +162,11 @@ __device__ __forceinline__ double u_real(double u, double a, double b) { return 
 // One getData() of asset i (DataSource.cpp).  `price` is the asset's current price
 // (== generator value for every synthetic source), gs points at gstate row gslot for
 // this env (stride N), pair_mean carries OUPair's shared mean from role 0 to role 1.
-// NOT inlined: one copy of the nine generator bodies per kernel (generic / Composite path).
+// NOT inlined: one copy of the nine generator bodies per kernel and draw source (generic / Composite path).
+// D provides N, draw_normal(d, slot), draw_uniform(d, slot).
+template <class D>
 static __device__ __noinline__ double gen_tick(const MdgAssetGen& g, double price, double* __restrict__ gs,
-                                               const GenCtx& d, double& pair_mean) {
+                                               D& d, double& pair_mean) {
   const double* p = g.p;
   const int64_t N = d.N;
   switch (g.type) {

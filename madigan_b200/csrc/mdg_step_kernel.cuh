@@ -206,7 +206,7 @@ __device__ __forceinline__ void shaper_add(const StepArgs& a, int64_t e, int c, 
   const double t_bm = q.bm[j];
 
 #ifndef MDG_MINB16
-#define MDG_MINB16 3
+#define MDG_MINB16 2
 #endif
 template <int CAP> constexpr size_t step_smem_bytes() { return sizeof(double) * (size_t)kBlock * ((CAP | 1) + CAP + (3 * CAP + 1) / 2); }
 
