@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 3
+#define MDG_ABI_VERSION 4
 #define MDG_MAX_ASSETS 16
 #define MDG_GEN_NPARAM 10
 #define MDG_MAX_NSTEP 64
@@ -141,6 +141,10 @@ typedef struct MdgState {
   double *shaper_B;   /* [ra][N] DSR/DDR moving second moment (nullable)   */
   double *nstep_ring; /* [nstep][ra][N] raw rewards waiting in the n-step buffer (nullable when nstep==1) */
   int32_t *nstep_len; /* [N] entries currently in the n-step buffer          (nullable when nstep==1) */
+  double *folds;      /* [5][N] cache of the portfolio's left-to-right folds at the current prices:
+                         assetValue, meanEntry.ledger, sum borrowedMargin, short entry value, and a
+                         magnitude bound.  Written by mdg_step / mdg_reset / mdg_init_state; call
+                         mdg_refresh_folds after modifying price/ledger/mean_entry/borrowed/cash from outside. */
 } MdgState;
 
 /* inputs and outputs of one step / reset */
@@ -233,6 +237,9 @@ int mdg_reset(const MdgParams *params, const MdgState *state, const MdgStepIO *i
  * empty ledger, cash=init_cash, timestamp=0, shaper state zero. */
 int mdg_init_state(const MdgParams *params, const MdgReward *reward, const MdgState *state,
                    const MdgLaunch *launch);
+
+/* Recompute MdgState.folds from the state tensors (after external writes into them). */
+int mdg_refresh_folds(const MdgParams *params, const MdgState *state, const MdgLaunch *launch);
 
 /* Portfolio's derived accounting for every env. */
 int mdg_derived(const MdgParams *params, const MdgState *state, const MdgDerived *out,

@@ -5,7 +5,7 @@ checks the struct sizes against the compiled library (``mdg_sizeof``).
 """
 import ctypes as C
 
-MDG_ABI_VERSION = 3
+MDG_ABI_VERSION = 4
 MDG_MAX_ASSETS = 16
 MDG_GEN_NPARAM = 10
 MDG_MAX_NSTEP = 64
@@ -58,7 +58,7 @@ class MdgReward(C.Structure):
 
 class MdgState(C.Structure):
     _fields_ = [(n, _dp) for n in ("price", "ledger", "mean_entry", "borrowed", "cash", "gstate",
-                                   "timestamp", "shaper_A", "shaper_B", "nstep_ring", "nstep_len")]
+                                   "timestamp", "shaper_A", "shaper_B", "nstep_ring", "nstep_len", "folds")]
 
 
 class MdgStepIO(C.Structure):
@@ -93,6 +93,7 @@ SYMBOLS = {
     "mdg_reset": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch), C.c_void_p,
                             C.c_int, C.c_int]),
     "mdg_init_state": (C.c_int, [_P(MdgParams), _P(MdgReward), _P(MdgState), _P(MdgLaunch)]),
+    "mdg_refresh_folds": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgLaunch)]),
     "mdg_derived": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgDerived), _P(MdgLaunch)]),
     "mdg_materialise_window": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,

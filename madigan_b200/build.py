@@ -1,8 +1,7 @@
 """Build ``madigan_b200/libmadigan_b200.so`` in-tree with nvcc for sm_100a.
 
 ``python -m madigan_b200.build`` (or ``__graft_entry__.build()``).  nvcc
-cross-compiles without a GPU; the five per-capacity instantiations of the fused
-step kernel are separate translation units so they compile in parallel.
+cross-compiles without a GPU; the two translation units compile in parallel.
 
 Flags that matter for parity: ``-fmad=false`` (no FMA contraction: the ledger's
 risk gates, and therefore the bit-exact positions, depend on every rounding).
@@ -51,10 +50,7 @@ def _deps_hash(src="", defs=()):
 
 
 def _units():
-    units = [("mdg_api.o", "mdg_api.cu", []), ("mdg_aux.o", "mdg_aux.cu", [])]
-    for cap in CAPS:
-        units.append((f"mdg_step_cap{cap}.o", "mdg_step_inst.cu", [f"-DMDG_CAP={cap}"]))
-    return units
+    return [("mdg_api.o", "mdg_api.cu", []), ("mdg_aux.o", "mdg_aux.cu", [])]
 
 
 def build(force=False, verbose=False, ptxas_info=False):
@@ -83,7 +79,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         return u, r
 
     # biggest unit first so the pool's critical path is the cap-16 kernel
-    units = sorted(todo, key=lambda u: -int(u[2][0].split("=")[1]) if u[2] else 0)
+    units = todo
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         results = list(ex.map(compile_one, units))
     log = []

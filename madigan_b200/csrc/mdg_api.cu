@@ -68,6 +68,13 @@ __global__ void __launch_bounds__(kResetBlock) reset_kernel(const __grid_constan
     const int64_t e = e0 + s_list[it];
     if (a.clear_nstep && a.S.nstep_len) a.S.nstep_len[e] = 0;  // offpolicy_q.py:94
     a.S.cash[e] = cash;
+    if (a.S.folds) {  // flat portfolio: every fold is a sum of zeros
+      a.S.folds[(int64_t)MDG_FOLD_AV * N + e] = 0.;
+      a.S.folds[(int64_t)MDG_FOLD_ML * N + e] = 0.;
+      a.S.folds[(int64_t)MDG_FOLD_BM * N + e] = 0.;
+      a.S.folds[(int64_t)MDG_FOLD_SE * N + e] = 0.;
+      a.S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(cash);
+    }
     const long long ts = a.S.timestamp[e];
     s_ts[it] = ts;
     a.S.timestamp[e] = ts + fill;
@@ -146,12 +153,43 @@ __global__ void __launch_bounds__(kBlock) init_kernel(const __grid_constant__ In
   }
   a.S.cash[e] = a.P.init_cash;
   a.S.timestamp[e] = 0;
+  if (a.S.folds) {
+    for (int r = 0; r < 4; ++r) a.S.folds[(int64_t)r * N + e] = 0.;
+    a.S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(a.P.init_cash);
+  }
   const int ra = a.R.reduce_rewards ? 1 : na;
   for (int c = 0; c < ra; ++c) {
     if (a.S.shaper_A) a.S.shaper_A[(int64_t)c * N + e] = 0.;
     if (a.S.shaper_B) a.S.shaper_B[(int64_t)c * N + e] = 0.;
   }
   if (a.S.nstep_len) a.S.nstep_len[e] = 0;
+}
+
+// exact left-to-right folds of the portfolio as stored (after external writes into the state tensors)
+struct FoldArgs {
+  MdgParams P;
+  MdgState S;
+  int64_t N;
+};
+__global__ void __launch_bounds__(kBlock) refresh_folds_kernel(const __grid_constant__ FoldArgs a) {
+  const int64_t N = a.N;
+  const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (e >= N) return;
+  double av = 0., ml = 0., bms = 0., se = 0., g = fabs(a.S.cash[e]);
+  for (int j = 0; j < a.P.n_assets; ++j) {
+    const double l = a.S.ledger[(int64_t)j * N + e], p = a.S.price[(int64_t)j * N + e],
+                 m = a.S.mean_entry[(int64_t)j * N + e], b = a.S.borrowed[(int64_t)j * N + e];
+    const double t_ml = m * l;
+    const double t_se = (l < 0.) ? t_ml : 0. * t_ml;
+    if (j == 0) { av = l * p; ml = t_ml; bms = b; se = t_se; }
+    else { av = av + l * p; ml = ml + t_ml; bms = bms + b; se = se + t_se; }
+    g += fabs(l * p) + fabs(t_ml) + fabs(b);
+  }
+  a.S.folds[(int64_t)MDG_FOLD_AV * N + e] = av;
+  a.S.folds[(int64_t)MDG_FOLD_ML * N + e] = ml;
+  a.S.folds[(int64_t)MDG_FOLD_BM * N + e] = bms;
+  a.S.folds[(int64_t)MDG_FOLD_SE * N + e] = se;
+  a.S.folds[(int64_t)MDG_FOLD_G * N + e] = g;
 }
 
 static int check_common(const MdgParams* P, const MdgLaunch* L) {
@@ -172,6 +210,7 @@ extern "C" int mdg_step(const MdgParams* P, const MdgReward* R, const MdgState* 
   int rc = check_common(P, L);
   if (rc) return rc;
   if (!S || !IO) return set_err(MDG_E_INVALID, "null state/io");
+  if (!S->folds) return set_err(MDG_E_INVALID, "state.folds is null");
   if (L->window < 1 || L->head < 0 || L->head >= L->window) return set_err(MDG_E_INVALID, "bad window/head");
   if (L->mode < MDG_MODE_HOLD || L->mode > MDG_MODE_SINGLE) return set_err(MDG_E_INVALID, "bad mode");
   if (L->mode != MDG_MODE_HOLD && !IO->units) return set_err(MDG_E_INVALID, "units is null");
@@ -195,11 +234,8 @@ extern "C" int mdg_step(const MdgParams* P, const MdgReward* R, const MdgState* 
     if (L->nstep_pos < 0 || L->nstep_pos >= a.R.nstep) return set_err(MDG_E_INVALID, "bad nstep_pos");
   }
   const int na = P->n_assets;
-  if (na == 1) return launch_step_cap1(a, true);
-  if (na == 2) return launch_step_cap2(a, true);
-  if (na <= 4) return launch_step_cap4(a, na == 4);
-  if (na <= 8) return launch_step_cap8(a, na == 8);
-  return launch_step_cap16(a, na == 16);
+  (void)na;
+  return launch_step(a);
 }
 
 extern "C" int mdg_reset(const MdgParams* P, const MdgState* S, const MdgStepIO* IO, const MdgLaunch* L,
@@ -231,6 +267,18 @@ extern "C" int mdg_init_state(const MdgParams* P, const MdgReward* R, const MdgS
   const unsigned grid = (unsigned)((L->n_envs + kBlock - 1) / kBlock);
   init_kernel<<<grid, kBlock, 0, (cudaStream_t)L->stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_init_state launch");
+}
+
+extern "C" int mdg_refresh_folds(const MdgParams* P, const MdgState* S, const MdgLaunch* L) {
+  int rc = check_common(P, L);
+  if (rc) return rc;
+  if (!S || !S->folds) return set_err(MDG_E_INVALID, "null state/folds");
+  if (L->n_envs == 0) return MDG_OK;
+  FoldArgs a;
+  a.P = *P; a.S = *S; a.N = L->n_envs;
+  const unsigned grid = (unsigned)((L->n_envs + kBlock - 1) / kBlock);
+  refresh_folds_kernel<<<grid, kBlock, 0, (cudaStream_t)L->stream>>>(a);
+  return cuda_err(cudaGetLastError(), "mdg_refresh_folds launch");
 }
 
 extern "C" int mdg_abi_version(void) { return MDG_ABI_VERSION; }

@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include "../../include/madigan_b200.h"
+#include "mdg_math.cuh"
 
 #define MDG_PI2 (3.141592653589793238463 * 2)  // DataSource.h:24
 
@@ -84,15 +85,15 @@ __device__ __forceinline__ void fill_normals(double* zcol, int zstride, int n_no
     return;
   }
   const int nb = (n_normals + 1) >> 1;
-#pragma unroll 2
+#pragma unroll 4
   for (int b = 0; b < nb; ++b) {
     uint64_t x0, x1;
     philox4x32_10(c.gid, (uint32_t)b, c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
     const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;  // (0,1)
     const double u2 = (double)(x1 >> 11) * 0x1.0p-53;          // [0,1)
-    const double r = sqrt(-2.0 * log(u1));
+    const double r = sqrt(-2.0 * fast_log_pos(u1));
     double sn, cs;
-    sincos(MDG_PI2 * u2, &sn, &cs);
+    fast_sincos_2pi(u2, sn, cs);
     zcol[(2 * b) * zstride] = r * cs;
     if (2 * b + 1 < n_normals) zcol[(2 * b + 1) * zstride] = r * sn;
   }
@@ -125,9 +126,9 @@ static __device__ __noinline__ double draw_normal(LazyDraws& c, int slot) {
     philox4x32_10(c.gid, (uint32_t)blk, c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
     const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
     const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
-    const double r = sqrt(-2.0 * log(u1));
+    const double r = sqrt(-2.0 * fast_log_pos(u1));
     double sn, cs;
-    sincos(MDG_PI2 * u2, &sn, &cs);
+    fast_sincos_2pi(u2, sn, cs);
     c.z0 = r * cs;
     c.z1 = r * sn;
     c.cached_block = blk;

@@ -1,8 +1,9 @@
 // Fused Env.step / Env.reset kernels for N independent environments (sm_100a).
 //
-// One thread per env; the whole portfolio (price, ledger, meanEntry, borrowedMargin
-// for up to 16 assets) lives in registers, state tensors are [rows][N] so every
-// load/store is one coalesced 256-byte run per warp.  One launch does what the
+// One thread per env STREAMS over its assets in a rolled loop: state tensors are
+// [rows][N], so every load/store is one coalesced 256-byte run per warp, each value is
+// read once, and the kernel is a few thousand instructions (an earlier fully unrolled,
+// register-resident version was I-cache bound, profiles/r1_notes.md).  One launch does what the
 // reference does across Env.h:189-256, Broker.cpp:124-178, Portfolio.cpp:140-323,
 // the DataSource.cpp getData family, offpolicy_q.py:140-164 and nstep_buffer.py:
 //   transact (sequential over assets, risk-gated) -> generator tick -> equity,
@@ -153,7 +154,7 @@ static __device__ __noinline__ double shaper_pop(const MdgReward& R, const NStep
 
 // ReplayBuffer.add (replay_buffer.py:68-80) + NStepBuffer.pop_nstep_sarsd (nstep_buffer.py:342-361)
 // for component c of env e: add `raw`, pop once when full, drain on done.
-__device__ __forceinline__ void shaper_add(const StepArgs& a, int64_t e, int c, int ra, double raw, bool done,
+static __device__ __noinline__ void shaper_add(const StepArgs& a, int64_t e, int c, int ra, double raw, bool done,
                                            int len_before, int& len_after, int& n_popped) {
   const MdgReward& R = a.R;
   const int64_t N = a.L.n_envs;
@@ -179,6 +180,7 @@ __device__ __forceinline__ void shaper_add(const StepArgs& a, int64_t e, int c, 
     ++first; ++k;
   }
   if (done) {
+#pragma unroll 1
     while (first < v.len) {
       a.IO.shaped_reward[((int64_t)k * ra + c) * N + e] = shaper_pop(R, v, first, A, B);
       ++first; ++k;
@@ -195,352 +197,452 @@ __device__ __forceinline__ void shaper_add(const StepArgs& a, int64_t e, int c, 
 // ---------------------------------------------------------------------------
 // the step kernel
 // ---------------------------------------------------------------------------
-#define MDG_GEN_GENERIC 0  // per-asset generator table, non-inlined generator bodies (Composite, Synth, trends ...)
-#define MDG_GEN_OUPAIRS 1  // every asset belongs to an OUPair (the headline workload): inlined pair update
+// rows of MdgState.folds
+#define MDG_FOLD_AV 0
+#define MDG_FOLD_ML 1
+#define MDG_FOLD_BM 2
+#define MDG_FOLD_SE 3
+#define MDG_FOLD_G 4
 
-// one term of the four folds for asset j
-#define MDG_TERMS(j)                                         \
-  const double t_av = q.led[j] * q.price[j];                 \
-  const double t_ml = q.mep[j] * q.led[j];                   \
-  const double t_se = (q.led[j] < 0.) ? t_ml : 0. * t_ml;    \
-  const double t_bm = q.bm[j];
+// Exact risk gate of asset i (Portfolio::checkRisk(i, units), Portfolio.cpp:254-279): every accounting
+// quantity is a left-to-right fold over the assets, exactly as in the oracle.  COLD path, called only when
+// the cheap bound in step_kernel cannot decide.  (pav..pse) are the folds over the already processed
+// assets 0..i-1 (final values); assets i.. are untouched so far and are re-read from global memory.
+static __device__ __noinline__ int exact_gate(const MdgState& S, int64_t N, int64_t e, int na, double cash,
+                                              double reqM, double maintM, int i, double units, double av,
+                                              double ml, double bms, double se) {
+#pragma unroll 1
+  for (int j = i; j < na; ++j) {
+    const double l = S.ledger[(int64_t)j * N + e], p = S.price[(int64_t)j * N + e],
+                 m = S.mean_entry[(int64_t)j * N + e], b = S.borrowed[(int64_t)j * N + e];
+    const double t_se = l * (m * (l < 0. ? 1. : 0.));
+    if (j == 0) { av = l * p; ml = m * l; bms = b; se = t_se; }
+    else { av = av + l * p; ml = ml + m * l; bms = bms + b; se = se + t_se; }
+  }
+  const double price = S.price[(int64_t)i * N + e], cur = S.ledger[(int64_t)i * N + e];
+  const bool opposite = (signbit(units) != 0) != (signbit(cur) != 0);
+  const double pnl = av - ml;        // :184-186
+  const double balance = cash + se;  // :192-197
+  const double availableMargin = (balance + pnl) / reqM;  // :229-231
+  if (opposite) {
+    const double excess = units + cur;
+    if (availableMargin <= fabs(price * excess) || balance <= 0.) return MDG_RISK_INSUFF_MARGIN;
+    return MDG_RISK_GREEN;
+  }
+  if (margin_call(cash, av, ml, bms, se, maintM)) return MDG_RISK_MARGIN_CALL;
+  if (availableMargin <= fabs(price * units) || balance <= 0.) return MDG_RISK_INSUFF_MARGIN;
+  return MDG_RISK_GREEN;
+}
 
-#ifndef MDG_MINB16
-#define MDG_MINB16 2
-#endif
-template <int CAP> constexpr size_t step_smem_bytes() { return sizeof(double) * (size_t)kBlock * ((CAP | 1) + CAP + (3 * CAP + 1) / 2); }
+// Registers of one env while it streams over its assets
+struct StepAcc {
+  double cash;
+  double rAV, rML, rBM, rSE, G;  // running sums (cheap risk bound) and their magnitude bound
+  double pav, pml, pbm, pse;     // exact left-to-right folds over the processed assets, old prices
+  double nav, gsum;              // exact fold of ledger*new price; magnitude sum for the next step
+  bool bad_risk;
+};
 
-template <int CAP, bool EXACT, int GENK>
-__global__ void __launch_bounds__(kBlock, (CAP >= 16 ? MDG_MINB16 : 4)) step_kernel(const __grid_constant__ StepArgs a) {
-  constexpr int US = CAP | 1;                 // odd row stride (doubles): conflict-free per-thread rows
-  constexpr int NZ = (3 * CAP + 1) / 2;       // normal draws per tick, worst case (all OU pairs)
-  // dynamic shared memory (57 KB at CAP=16, above the 48 KB static limit), see step_smem_bytes()
-  extern __shared__ double smem_dyn[];
-  double* s_units = smem_dyn;                                                   // [kBlock*US] units, later mar_diff (offpolicy_q.py:154)
-  double (*s_prev)[kBlock] = reinterpret_cast<double (*)[kBlock]>(smem_dyn + kBlock * US);        // [CAP] prev position values, later reward numerators
-  double (*s_z)[kBlock] = reinterpret_cast<double (*)[kBlock]>(smem_dyn + kBlock * US + CAP * kBlock);  // [NZ] this tick's normal draws
+struct StepConsts {
+  double reqM, maintM, band_scale;
+  bool reqM_ok;
+};
 
+// Broker::handleTransaction(port, i, units) (Broker.cpp:124-142) for one asset whose state is in registers:
+// risk gate (Portfolio.cpp:254-279), slippage/cost (Broker.cpp:171-178), ledger update (Portfolio.cpp:284-323).
+//
+// The gate compares folds over the whole portfolio with thresholds.  Recomputing the folds per asset is
+// O(nA^2) fp64 work, so the gate first uses RUNNING sums (O(1) update per transaction, hence rounded
+// differently from a fresh fold) with a rigorous bound: running and exact folds differ by < 1e-13 * G
+// (G = sum of magnitudes); a decision is taken from the running sums only when it clears its threshold by
+// 1e-9 * G.  Otherwise -- a knife-edge, NaN/Inf, a non-positive required margin -- the exact left-to-right
+// folds decide (exact_gate).  Decisions, and therefore ledgers, are bit-identical to the oracle's either way.
+__device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c, StepAcc& A, int64_t N, int64_t e,
+                                         int na, int i, double price, double& cur, double& mep, double& bm,
+                                         double units, double& tp, double& tu, double& tc, int& risk,
+                                         double& prev_val) {
   const MdgParams& P = a.P;
+  const MdgState& S = a.S;
+  prev_val = cur * price;  // offpolicy_q.py:141
+  tp = 0.; tu = 0.; tc = 0.;
+  risk = MDG_RISK_GREEN;
+  if (units != 0.) {  // Broker.cpp:126 (NaN units do enter, as in the reference)
+    const bool opposite = (signbit(units) != 0) != (signbit(cur) != 0);
+    if (!opposite || units > -1 * cur) {  // Portfolio.cpp:257-258: only these orders are gated
+      const double amt = fabs(price * (opposite ? units + cur : units));
+      const double bal = A.cash + A.rSE, pnl = A.rAV - A.rML, x = bal + pnl;
+      const double band = c.band_scale * (A.G + amt);
+      const double d1 = x - amt * c.reqM;  // availableMargin <= |amount|  <=>  d1 <= 0
+      bool certain = c.reqM_ok && fabs(d1) > band && fabs(bal) > band;
+      int r_fast = (d1 <= 0. || bal <= 0.) ? MDG_RISK_INSUFF_MARGIN : MDG_RISK_GREEN;
+      if (!opposite) {  // Portfolio::checkRisk() first (:268), :243-252
+        const double m = c.maintM * pnl;
+        const double d3 = (A.cash + A.rAV - A.rBM) + m, d4 = x + m;
+        certain = certain && fabs(d3) > band && fabs(d4) > band;
+        if (d3 <= 0. || d4 <= 0.) r_fast = MDG_RISK_MARGIN_CALL;
+      }
+      risk = certain ? r_fast
+                     : exact_gate(S, N, e, na, A.cash, c.reqM, c.maintM, i, units, A.pav, A.pml, A.pbm, A.pse);
+    }
+    if (risk == MDG_RISK_GREEN) {
+      // Broker::applySlippage / getTransactionCost  Broker.cpp:171-178
+      const double slippage = (price * P.slippage_rel) + P.slippage_abs;
+      const double transactionPrice = units < 0 ? (price - slippage) : (price + slippage);
+      const double transactionCost = fabs(units * price) * P.tcost_rel + P.tcost_abs;
+      tp = transactionPrice; tu = units; tc = transactionCost;
+      // Portfolio::handleTransaction  Portfolio.cpp:284-323
+      const double o_ml = mep * cur, o_bm = bm;
+      const double o_se = (cur < 0.) ? o_ml : 0.;
+      if (opposite) {
+        if (fabs(units) > fabs(cur)) {
+          units += cur;
+          A.cash += cur * transactionPrice;
+          cur = 0.;
+          mep = transactionPrice;
+        }
+      } else {
+        mep += (transactionPrice - mep) * (units / (units + cur));
+      }
+      const double amount = transactionPrice * units;
+      const double marginToUse = amount * c.reqM;
+      const double marginToBorrow = amount - marginToUse;
+      bm += marginToBorrow;
+      A.cash -= (marginToUse + transactionCost);
+      cur += units;
+      if (fabs(cur) < 0.000001) {
+        mep = 0.;
+        if (bm > 0.) { A.cash -= bm; bm = 0.; }
+      }
+      if (bm < 0.) { A.cash -= bm; bm = 0.; }
+      S.ledger[(int64_t)i * N + e] = cur;
+      S.mean_entry[(int64_t)i * N + e] = mep;
+      S.borrowed[(int64_t)i * N + e] = bm;
+      // running sums and their magnitude bound
+      const double n_av = cur * price, n_ml = mep * cur;
+      A.rAV += n_av - prev_val;
+      A.rML += n_ml - o_ml;
+      A.rBM += bm - o_bm;
+      A.rSE += ((cur < 0.) ? n_ml : 0.) - o_se;
+      A.G += fabs(n_av) + fabs(n_ml) + fabs(bm) + fabs(amount) + fabs(transactionCost) + fabs(o_bm);
+    } else if (risk != MDG_RISK_INSUFF_MARGIN) {
+      A.bad_risk = true;
+    }
+  }
+  if (a.L.mode != MDG_MODE_HOLD) {
+    a.IO.trans_price[(int64_t)i * N + e] = tp;
+    a.IO.trans_units[(int64_t)i * N + e] = tu;
+    a.IO.trans_cost[(int64_t)i * N + e] = tc;
+    a.IO.risk[(int64_t)i * N + e] = (uint8_t)risk;
+  }
+  // exact folds of the final ledger, old prices (Portfolio.cpp:180-197,207-209)
+  const double t_ml = mep * cur;
+  const double t_se = (cur < 0.) ? t_ml : 0. * t_ml;
+  if (i == 0) { A.pav = cur * price; A.pml = t_ml; A.pbm = bm; A.pse = t_se; }
+  else { A.pav = A.pav + cur * price; A.pml = A.pml + t_ml; A.pbm = A.pbm + bm; A.pse = A.pse + t_se; }
+  A.gsum += fabs(t_ml) + fabs(bm);
+}
+
+// after the tick of asset i: state/observation stores, fold of the new position value, reward stash
+__device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t N, int64_t e, int na, int i,
+                                          double cur, double newp, double prev_val, double tp, double tu,
+                                          double tc, double* st_cur, double* st_pm) {
+  a.S.price[(int64_t)i * N + e] = newp;
+  a.IO.obs_price[((int64_t)a.L.head * na + i) * N + e] = newp;  // State.price row (Env.h:202,228,254)
+  const double cur_val = cur * newp;
+  A.nav = (i == 0) ? cur_val : A.nav + cur_val;
+  A.gsum += fabs(cur_val);
+  st_cur[(int64_t)i * kBlock] = cur_val;
+  st_pm[(int64_t)i * kBlock] = prev_val + (tu * tp + tc);  // prev_val + mar_diff, offpolicy_q.py:153-156
+}
+
+// in-order normal draws for the all-OU-pairs kernel: one Philox block = two normals (same (block, lane)
+// addressing as draw_normal: slot s -> block s>>1, lane s&1; slots are consumed in increasing order)
+struct NormalFifo {
+  double zb;     // lane 1 of the current block, not yet consumed
+  int have;      // 1 if zb is valid
+  uint32_t blk;  // next Philox block
+};
+__device__ __forceinline__ double next_normal(NormalFifo& f, uint32_t gid, uint32_t t_lo, uint32_t t_hi,
+                                              uint32_t k0, uint32_t k1) {
+  if (f.have) {
+    f.have = 0;
+    return f.zb;
+  }
+  uint64_t x0, x1;
+  philox4x32_10(gid, f.blk, t_lo, t_hi, k0, k1, x0, x1);
+  f.blk += 1;
+  const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
+  const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
+  const double r = sqrt(-2.0 * fast_log_pos(u1));
+  double sn, cs;
+  fast_sincos_2pi(u2, sn, cs);
+  f.zb = r * sn;
+  f.have = 1;
+  return r * cs;
+}
+
+constexpr int kStepMinBlocks = 4;  // 512 threads / SM: <= 128 registers (no spills), 2*nA*8 B of shared memory per thread
+
+template <bool PAIRS>
+__global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __grid_constant__ StepArgs a) {
+  // per-thread stash, [2*nA][kBlock]: position value after the tick, and prev value + mar_diff
+  extern __shared__ double stash[];
+  const MdgParams& P = a.P;
+  const MdgState& S = a.S;
   const int64_t N = a.L.n_envs;
-  const int na = EXACT ? CAP : P.n_assets;
+  const int na = P.n_assets;
   const int tid = threadIdx.x;
-  const int64_t e0 = (int64_t)blockIdx.x * kBlock;
-  const int64_t e = e0 + tid;
-  const bool active = e < N;
+  const int64_t e = (int64_t)blockIdx.x * kBlock + tid;
+  if (e >= N) return;
   const int mode = a.L.mode;
-
-  // stage this block's (rows, na) slice of the row-major units matrix through smem (coalesced)
-  if (mode == MDG_MODE_MULTI) {
-    const int64_t rows = (N - e0) < kBlock ? (N - e0) : kBlock;
-    const int total = (int)rows * na;
-    const double* src = a.IO.units + e0 * na;
-    for (int idx = tid; idx < total; idx += kBlock) {
-      const int r = idx / na, c = idx - r * na;
-      s_units[r * US + c] = src[idx];
-    }
-  } else if (mode == MDG_MODE_SINGLE) {
-    if (active) s_units[tid * US] = a.IO.units[e];
-  }
-  __syncthreads();
-  if (!active) return;
-
-  // ---- load state (all loads issued before the RNG loop below, which hides their latency)
-  Port<CAP> q;
-#pragma unroll
-  for (int j = 0; j < CAP; ++j) {
-    if (EXACT || j < na) {
-      q.price[j] = a.S.price[(int64_t)j * N + e];
-      q.led[j] = a.S.ledger[(int64_t)j * N + e];
-      q.mep[j] = a.S.mean_entry[(int64_t)j * N + e];
-      q.bm[j] = a.S.borrowed[(int64_t)j * N + e];
-    } else {
-      q.price[j] = 0.; q.led[j] = 0.; q.mep[j] = 0.; q.bm[j] = 0.;
-    }
-  }
-  q.cash = a.S.cash[e];
-  const int64_t ts = a.S.timestamp[e];
   const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
+  double* st_cur = stash + tid;                        // [j * kBlock]
+  double* st_pm = stash + (int64_t)na * kBlock + tid;  // [j * kBlock]
+  const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;
 
-  // ---- this tick's normal draws (Philox4x32-10 + Box-Muller, or the injected stream)
-  GenCtx ctx;
-  ctx_init(ctx, &s_z[0][tid], kBlock, a.IO.uniforms, a.L, e, ts);
-  fill_normals(&s_z[0][tid], kBlock, P.n_normals, a.IO.normals, ctx);
+  StepAcc A;
+  A.cash = S.cash[e];
+  const int64_t ts = S.timestamp[e];
+  // Folds of the incoming portfolio.  They are exactly the folds this kernel (or reset/init/refresh)
+  // computed at the end of the previous call -- same values, same left-to-right order -- so they are
+  // carried in state instead of re-reading the whole portfolio before the first transaction.
+  A.rAV = S.folds[(int64_t)MDG_FOLD_AV * N + e];
+  A.rML = S.folds[(int64_t)MDG_FOLD_ML * N + e];
+  A.rBM = S.folds[(int64_t)MDG_FOLD_BM * N + e];
+  A.rSE = S.folds[(int64_t)MDG_FOLD_SE * N + e];
+  A.G = S.folds[(int64_t)MDG_FOLD_G * N + e];
+  A.pav = A.pml = A.pbm = A.pse = A.nav = A.gsum = 0.;
+  A.bad_risk = false;
+  const double prevEq = A.cash + A.rAV - A.rBM;  // Env.h:190,208,234
 
-  // ---- prevEq (Env.h:190,208,234) and previous position values (offpolicy_q.py:140-141)
-  double prevEq;
-  {
-    double av = 0., bms = 0.;
+  StepConsts c;
+  c.reqM = P.required_margin;
+  c.maintM = P.maintenance_margin;
+  c.reqM_ok = c.reqM > 0. && c.reqM <= 1e6;
+  c.band_scale = 1e-9 * (1. + fabs(c.maintM)) * (c.reqM > 1. ? c.reqM : 1.);
+
+  const uint32_t gid = (uint32_t)(a.L.env_offset + e);
+  const uint32_t k0 = (uint32_t)a.L.seed, k1 = (uint32_t)(a.L.seed >> 32);
+  const uint32_t t_lo = (uint32_t)(uint64_t)ts, t_hi = (uint32_t)((uint64_t)ts >> 32);
+
+  if (PAIRS) {
+    // ---- headline path: every asset belongs to an OU pair.  One iteration = one pair; the next pair's
+    // state and units are loaded while the current pair is processed (software prefetch).
+    const int np = na >> 1;
+    NormalFifo fifo;
+    fifo.zb = 0.; fifo.have = 0; fifo.blk = 0;
+    double n_price[2], n_cur[2], n_mep[2], n_bm[2], n_units[2], n_mean;
 #pragma unroll
-    for (int j = 0; j < CAP; ++j) {
-      if (EXACT || j < na) {
-        const double t = q.led[j] * q.price[j];
-        if (j == 0) { av = t; bms = q.bm[0]; } else { av = av + t; bms = bms + q.bm[j]; }
-        if (shaping) s_prev[j][tid] = t;
-      }
+    for (int q = 0; q < 2; ++q) {
+      n_price[q] = S.price[(int64_t)q * N + e];
+      n_cur[q] = S.ledger[(int64_t)q * N + e];
+      n_mep[q] = S.mean_entry[(int64_t)q * N + e];
+      n_bm[q] = S.borrowed[(int64_t)q * N + e];
+      n_units[q] = (mode == MDG_MODE_MULTI) ? urow[q] : 0.;
     }
-    prevEq = q.cash + av - bms;
-  }
-
-  // ---- transactions, sequential over assets (Broker.cpp:124-158, Portfolio.cpp:254-323).
-  // Every accounting quantity is a left-to-right fold over the assets.  Asset i's risk gate sees
-  // final values for assets < i and untouched values for assets >= i, so the fold is kept as a
-  // running PREFIX over processed assets and only the suffix i..nA-1 is re-added: the same
-  // operations in the same order as a full recomputation (bit-identical), at half the work.
-  double pav = 0., pml = 0., pbm = 0., pse = 0.;
-  bool bad_risk = false;
+    n_mean = S.gstate[(int64_t)P.gen[0].gslot * N + e];
+#pragma unroll 1
+    for (int p = 0; p < np; ++p) {
+      double price[2], cur[2], mep[2], bm[2], units[2], prev_val[2], tp[2], tu[2], tc[2];
+      int risk[2];
+      double mean = n_mean;
 #pragma unroll
-  for (int i = 0; i < CAP; ++i) {
-    if (EXACT || i < na) {
-      double tp = 0., tu = 0., tc = 0.;
-      int risk = MDG_RISK_GREEN;
-      double units = 0.;
-      if (mode == MDG_MODE_MULTI) units = s_units[tid * US + i];
-      else if (mode == MDG_MODE_SINGLE && i == a.L.asset_idx) units = s_units[tid * US];
-      if (units != 0.) {  // Broker.cpp:126 (NaN units do enter, as in the reference)
-        const double price = q.price[i];
-        double cur = q.led[i];
-        const bool opposite = (signbit(units) != 0) != (signbit(cur) != 0);
-        if (!opposite || units > -1 * cur) {  // Portfolio.cpp:257-258: only these orders are gated
-          double av = pav, ml = pml, bms = pbm, se = pse;
+      for (int q = 0; q < 2; ++q) {
+        price[q] = n_price[q]; cur[q] = n_cur[q]; mep[q] = n_mep[q]; bm[q] = n_bm[q]; units[q] = n_units[q];
+      }
+      if (p + 1 < np) {
 #pragma unroll
-          for (int j = i; j < CAP; ++j) {
-            if (EXACT || j < na) {
-              MDG_TERMS(j)
-              if (j == 0) { av = t_av; ml = t_ml; bms = t_bm; se = t_se; }
-              else { av = av + t_av; ml = ml + t_ml; bms = bms + t_bm; se = se + t_se; }
-            }
-          }
-          const double pnl = av - ml;           // :184-186
-          const double balance = q.cash + se;   // :192-197
-          const double availableMargin = (balance + pnl) / P.required_margin;  // :229-231
-          if (opposite) {
-            const double excess = units + cur;
-            if (availableMargin <= fabs(price * excess) || balance <= 0.) risk = MDG_RISK_INSUFF_MARGIN;
-          } else if (margin_call(q.cash, av, ml, bms, se, P.maintenance_margin)) {
-            risk = MDG_RISK_MARGIN_CALL;
-          } else {
-            const double cashAmount = price * units;
-            if (availableMargin <= fabs(cashAmount) || balance <= 0.) risk = MDG_RISK_INSUFF_MARGIN;
-          }
+        for (int q = 0; q < 2; ++q) {
+          const int j = 2 * p + 2 + q;
+          n_price[q] = S.price[(int64_t)j * N + e];
+          n_cur[q] = S.ledger[(int64_t)j * N + e];
+          n_mep[q] = S.mean_entry[(int64_t)j * N + e];
+          n_bm[q] = S.borrowed[(int64_t)j * N + e];
+          n_units[q] = (mode == MDG_MODE_MULTI) ? urow[j] : 0.;
         }
-        if (risk == MDG_RISK_GREEN) {
-          // Broker::applySlippage / getTransactionCost  Broker.cpp:171-178
-          const double slippage = (price * P.slippage_rel) + P.slippage_abs;
-          const double transactionPrice = units < 0 ? (price - slippage) : (price + slippage);
-          const double transactionCost = fabs(units * price) * P.tcost_rel + P.tcost_abs;
-          tp = transactionPrice; tu = units; tc = transactionCost;
-          // Portfolio::handleTransaction  Portfolio.cpp:284-323
-          double mep = q.mep[i];
-          if (opposite) {
-            if (fabs(units) > fabs(cur)) {
-              units += cur;
-              q.cash += cur * transactionPrice;
-              cur = 0.;
-              mep = transactionPrice;
-            }
-          } else {
-            mep += (transactionPrice - mep) * (units / (units + cur));
-          }
-          const double amount = transactionPrice * units;
-          const double marginToUse = amount * P.required_margin;
-          const double marginToBorrow = amount - marginToUse;
-          double bm = q.bm[i];
-          bm += marginToBorrow;
-          q.cash -= (marginToUse + transactionCost);
-          cur += units;
-          if (fabs(cur) < 0.000001) {
-            mep = 0.;
-            if (bm > 0.) { q.cash -= bm; bm = 0.; }
-          }
-          if (bm < 0.) { q.cash -= bm; bm = 0.; }
-          q.led[i] = cur; q.mep[i] = mep; q.bm[i] = bm;
-        } else if (risk != MDG_RISK_INSUFF_MARGIN) {
-          bad_risk = true;
-        }
+        n_mean = S.gstate[(int64_t)P.gen[2 * p + 2].gslot * N + e];
       }
-      {  // extend the prefix folds with asset i's final values
-        MDG_TERMS(i)
-        if (i == 0) { pav = t_av; pml = t_ml; pbm = t_bm; pse = t_se; }
-        else { pav = pav + t_av; pml = pml + t_ml; pbm = pbm + t_bm; pse = pse + t_se; }
-      }
-      if (mode != MDG_MODE_HOLD) {
-        a.IO.trans_price[(int64_t)i * N + e] = tp;
-        a.IO.trans_units[(int64_t)i * N + e] = tu;
-        a.IO.trans_cost[(int64_t)i * N + e] = tc;
-        a.IO.risk[(int64_t)i * N + e] = (uint8_t)risk;
-        if (shaping) s_units[tid * US + i] = tu * tp + tc;  // mar_diff, offpolicy_q.py:154-155
-      }
-    }
-  }
-  // BrokerResponse.marginCall (Broker.cpp:135,156): Portfolio::checkRisk() after the last transaction
-  if (mode != MDG_MODE_HOLD)
-    a.IO.margin_call[e] = margin_call(q.cash, pav, pml, pbm, pse, P.maintenance_margin) ? 1 : 0;
-
-  // ---- write back the ledger (prices follow after the tick)
 #pragma unroll
-  for (int j = 0; j < CAP; ++j) {
-    if (EXACT || j < na) {
-      a.S.ledger[(int64_t)j * N + e] = q.led[j];
-      a.S.mean_entry[(int64_t)j * N + e] = q.mep[j];
-      a.S.borrowed[(int64_t)j * N + e] = q.bm[j];
-    }
-  }
-  a.S.cash[e] = q.cash;
-
-  // ---- generator tick (DataSource.cpp getData family)
-  if (GENK == MDG_GEN_OUPAIRS) {
-#pragma unroll
-    for (int p = 0; p < CAP / 2; ++p) {  // OUPair::getData, DataSource.cpp:1232-1240 (draw order rw, x0, x1)
+      for (int q = 0; q < 2; ++q) {
+        const int i = 2 * p + q;
+        if (mode == MDG_MODE_SINGLE) units[q] = (i == a.L.asset_idx) ? urow[0] : 0.;
+        tx_asset(a, c, A, N, e, na, i, price[q], cur[q], mep[q], bm[q], units[q], tp[q], tu[q], tc[q], risk[q],
+                 prev_val[q]);
+      }
+      // OUPair::getData, DataSource.cpp:1232-1240 (draw order rw, x0, x1)
       const MdgAssetGen& g0 = P.gen[2 * p];
       const MdgAssetGen& g1 = P.gen[2 * p + 1];
-      double* mrow = a.S.gstate + (int64_t)g0.gslot * N + e;
-      double m = *mrow;
-      m += m * (draw_normal(ctx, g0.nslot_aux) * g0.p[2]);
-      *mrow = m;
-      q.price[2 * p] += (g0.p[0] * (m - q.price[2 * p])) + m * (draw_normal(ctx, g0.nslot) * g0.p[1]);
-      q.price[2 * p + 1] += (g1.p[0] * (m - q.price[2 * p + 1])) + m * (draw_normal(ctx, g1.nslot) * g1.p[1]);
+      double z_rw, z0, z1;
+      if (a.IO.normals) {
+        z_rw = a.IO.normals[(int64_t)g0.nslot_aux * N + e];
+        z0 = a.IO.normals[(int64_t)g0.nslot * N + e];
+        z1 = a.IO.normals[(int64_t)g1.nslot * N + e];
+      } else {
+        z_rw = next_normal(fifo, gid, t_lo, t_hi, k0, k1);
+        z0 = next_normal(fifo, gid, t_lo, t_hi, k0, k1);
+        z1 = next_normal(fifo, gid, t_lo, t_hi, k0, k1);
+      }
+      mean += mean * (z_rw * g0.p[2]);
+      S.gstate[(int64_t)g0.gslot * N + e] = mean;
+      const double newp0 = price[0] + ((g0.p[0] * (mean - price[0])) + mean * (z0 * g0.p[1]));
+      const double newp1 = price[1] + ((g1.p[0] * (mean - price[1])) + mean * (z1 * g1.p[1]));
+      post_tick(a, A, N, e, na, 2 * p, cur[0], newp0, prev_val[0], tp[0], tu[0], tc[0], st_cur, st_pm);
+      post_tick(a, A, N, e, na, 2 * p + 1, cur[1], newp1, prev_val[1], tp[1], tu[1], tc[1], st_cur, st_pm);
     }
   } else {
+    // ---- generic path (Composite / sine / trend sources): one asset per iteration
+    LazyDraws dr;
+    dr.N = N; dr.e = e;
+    dr.gid = gid; dr.k0 = k0; dr.k1 = k1; dr.t_lo = t_lo; dr.t_hi = t_hi;
+    dr.cached_block = -1;
+    dr.normals = a.IO.normals; dr.uniforms = a.IO.uniforms;
     double pair_mean = 0.;
-#pragma unroll
-    for (int i = 0; i < CAP; ++i) {
-      if (EXACT || i < na) {
-        const MdgAssetGen& g = P.gen[i];
-        double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-        q.price[i] = gen_tick(g, q.price[i], gs, ctx, pair_mean);
+#pragma unroll 1
+    for (int i = 0; i < na; ++i) {
+      const double price = S.price[(int64_t)i * N + e];
+      double cur = S.ledger[(int64_t)i * N + e];
+      double mep = S.mean_entry[(int64_t)i * N + e];
+      double bm = S.borrowed[(int64_t)i * N + e];
+      double units = 0.;
+      if (mode == MDG_MODE_MULTI) units = urow[i];
+      else if (mode == MDG_MODE_SINGLE && i == a.L.asset_idx) units = urow[0];
+      double tp, tu, tc, prev_val;
+      int risk;
+      tx_asset(a, c, A, N, e, na, i, price, cur, mep, bm, units, tp, tu, tc, risk, prev_val);
+      // generator tick of this asset (DataSource.cpp getData family)
+      const MdgAssetGen& g = P.gen[i];
+      double newp;
+      if (g.type == MDG_GEN_OUPAIR) {  // OUPair::getData :1232-1240 (draw order rw, x0, x1)
+        if (g.role == 0) {
+          double* mrow = S.gstate + (int64_t)g.gslot * N + e;
+          double m = *mrow;
+          m += m * (draw_normal(dr, g.nslot_aux) * g.p[2]);
+          *mrow = m;
+          pair_mean = m;
+        }
+        newp = price + ((g.p[0] * (pair_mean - price)) + pair_mean * (draw_normal(dr, g.nslot) * g.p[1]));
+      } else if (g.type == MDG_GEN_OU) {  // OU::getData :1173-1180
+        newp = price + ((g.p[1] * (g.p[0] - price)) + g.p[0] * g.p[2] * draw_normal(dr, g.nslot));
+      } else {
+        double* gs = S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
+        newp = gen_tick(g, price, gs, dr, pair_mean);
       }
+      post_tick(a, A, N, e, na, i, cur, newp, prev_val, tp, tu, tc, st_cur, st_pm);
     }
   }
-  a.S.timestamp[e] = ts + 1;
 
-  // ---- equity, reward, done (Env.h:192-198, 211-223, 237-249); only the price-dependent fold changes
-  double av = 0.;
-#pragma unroll
-  for (int j = 0; j < CAP; ++j) {
-    if (EXACT || j < na) {
-      a.S.price[(int64_t)j * N + e] = q.price[j];
-      const double t = q.led[j] * q.price[j];
-      av = (j == 0) ? t : av + t;
-    }
-  }
-  const double currentEq = q.cash + av - pbm;
+  const double cash = A.cash, nav = A.nav, pml = A.pml, pbm = A.pbm, pse = A.pse, maintM = c.maintM;
+  const int head = a.L.head;
+  // BrokerResponse.marginCall (Broker.cpp:135,156): Portfolio::checkRisk() after the last transaction
+  if (mode != MDG_MODE_HOLD) a.IO.margin_call[e] = margin_call(cash, A.pav, pml, pbm, pse, maintM) ? 1 : 0;
+  S.cash[e] = cash;
+  S.timestamp[e] = ts + 1;
+  S.folds[(int64_t)MDG_FOLD_AV * N + e] = nav;
+  S.folds[(int64_t)MDG_FOLD_ML * N + e] = pml;
+  S.folds[(int64_t)MDG_FOLD_BM * N + e] = pbm;
+  S.folds[(int64_t)MDG_FOLD_SE * N + e] = pse;
+  S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(cash) + A.gsum;
+  const bool bad_risk = A.bad_risk;
+
+  // ---- equity, reward, done (Env.h:192-198, 211-223, 237-249)
+  const double currentEq = cash + nav - pbm;
   const double clampv = (mode == MDG_MODE_SINGLE) ? 0.01 : 0.3;
-  a.IO.reward[e] = log(dmax(currentEq / prevEq, clampv));
-  const bool mc = margin_call(q.cash, av, pml, pbm, pse, P.maintenance_margin);
+  a.IO.reward[e] = fast_log(dmax(currentEq / prevEq, clampv));
+  const bool mc = margin_call(cash, nav, pml, pbm, pse, maintM);
   bool done = mc || (currentEq < 0.1 * P.init_cash);
   if (mode != MDG_MODE_HOLD) done = done || bad_risk;
   a.IO.done[e] = done ? 1 : 0;
 
-  // ---- newest observation row: State(price, ledgerNormedFull, timestamp)  (Env.h:202,228,254).
-  // Observations carry a 1e-9 bar (not bit-exactness), so the nA+1 divisions by equity are one
-  // reciprocal and nA+1 multiplies.
-  const int head = a.L.head;
+  // ---- State.portfolio row = ledgerNormedFull (Portfolio.cpp:150-155).  Observations carry a 1e-9 bar
+  // (not bit-exactness): the nA+1 divisions by equity are one reciprocal and nA+1 multiplies.
   const double inv_eq = 1. / currentEq;
-  double cosv_pp = 0., cosv_qq = 0., cosv_pq = 0.;
   const bool cosine = shaping && a.R.shaper == MDG_SHAPER_COSINE;
+  double cosv_pp = 0., cosv_qq = 0., cosv_pq = 0.;
   {
-    const double w0 = (q.cash - pbm) * inv_eq;  // Portfolio.cpp:150-155
+    const double w0 = (cash - pbm) * inv_eq;
     a.IO.obs_port[((int64_t)head * (na + 1)) * N + e] = w0;
     if (cosine) {
       const double d0 = a.R.desired_portfolio[0];
       cosv_pp = w0 * w0; cosv_qq = d0 * d0; cosv_pq = w0 * d0;
     }
-#pragma unroll
-    for (int j = 0; j < CAP; ++j) {
-      if (EXACT || j < na) {
-        const double cur_val = q.led[j] * q.price[j];
-        const double w = cur_val * inv_eq;
-        a.IO.obs_price[((int64_t)head * na + j) * N + e] = q.price[j];
-        a.IO.obs_port[((int64_t)head * (na + 1) + j + 1) * N + e] = w;
-        if (cosine) {
-          const double dj = a.R.desired_portfolio[j + 1];
-          cosv_pp = cosv_pp + w * w; cosv_qq = cosv_qq + dj * dj; cosv_pq = cosv_pq + w * dj;
-        }
-        // numerator of the agent reward: curr_val - prev_val - mar_diff (offpolicy_q.py:156)
-        if (shaping) s_prev[j][tid] = cur_val - s_prev[j][tid] - s_units[tid * US + j];
-      }
-    }
-    a.IO.obs_time[(int64_t)head * N + e] = ts + 1;
   }
-
-  // ---- agent reward (offpolicy_q.py:152-164) and the n-step shaper; a rolled loop over assets
-  if (shaping) {
-    const int ra = a.R.reduce_rewards ? 1 : na;
-    double extra = 0.;
-    if (cosine) extra = a.R.cosine_temp * (cosv_pq / (sqrt(cosv_pp) * sqrt(cosv_qq)));  // nstep_buffer.py:173-191
-    const int len_before = (a.R.nstep > 1) ? a.S.nstep_len[e] : 0;
-    const double inv_prev = 1. / prevEq;
-    int len_after = 0, n_popped = 0;
-    double rsum = 0.;
-#pragma unroll 1
-    for (int j = 0; j < na; ++j) {
-      double x = s_prev[j][tid] * inv_prev;
+  a.IO.obs_time[(int64_t)head * N + e] = ts + 1;
+  const int ra = a.R.reduce_rewards ? 1 : na;
+  const double inv_prev = 1. / prevEq;
+  const int len_before = (shaping && a.R.nstep > 1) ? S.nstep_len[e] : 0;
+  int len_after = 0, n_popped = 0;
+  double rsum = 0.;
+#pragma unroll 2
+  for (int j = 0; j < na; ++j) {
+    const double cur_val = st_cur[(int64_t)j * kBlock];
+    const double w = cur_val * inv_eq;
+    a.IO.obs_port[((int64_t)head * (na + 1) + j + 1) * N + e] = w;
+    if (cosine) {
+      const double dj = a.R.desired_portfolio[j + 1];
+      cosv_pp = cosv_pp + w * w; cosv_qq = cosv_qq + dj * dj; cosv_pq = cosv_pq + w * dj;
+    }
+    if (shaping && !cosine) {  // agent reward (offpolicy_q.py:152-164); with the cosine shaper see below
+      double x = (cur_val - st_pm[(int64_t)j * kBlock]) * inv_prev;
       x += 1;
-      const double r = log((x != x) ? x : ((x < .35) ? .35 : x));
+      const double r = fast_log((x != x) ? x : ((x < .35) ? .35 : x));
       if (a.R.reduce_rewards) {
         rsum = (j == 0) ? r : rsum + r;
       } else {
         a.IO.agent_reward[(int64_t)j * N + e] = r;
-        shaper_add(a, e, j, ra, cosine ? r + extra : r, done, len_before, len_after, n_popped);
+        shaper_add(a, e, j, ra, r, done, len_before, len_after, n_popped);
+      }
+    }
+  }
+  if (cosine) {  // the PPC term needs the whole portfolio row first (nstep_buffer.py:173-191)
+    const double extra = a.R.cosine_temp * (cosv_pq / (sqrt(cosv_pp) * sqrt(cosv_qq)));
+#pragma unroll 1
+    for (int j = 0; j < na; ++j) {
+      double x = (st_cur[(int64_t)j * kBlock] - st_pm[(int64_t)j * kBlock]) * inv_prev;
+      x += 1;
+      const double r = fast_log((x != x) ? x : ((x < .35) ? .35 : x));
+      if (a.R.reduce_rewards) {
+        rsum = (j == 0) ? r : rsum + r;
+      } else {
+        a.IO.agent_reward[(int64_t)j * N + e] = r;
+        shaper_add(a, e, j, ra, r + extra, done, len_before, len_after, n_popped);
       }
     }
     if (a.R.reduce_rewards) {
       a.IO.agent_reward[e] = rsum;
-      shaper_add(a, e, 0, 1, cosine ? rsum + extra : rsum, done, len_before, len_after, n_popped);
+      shaper_add(a, e, 0, 1, rsum + extra, done, len_before, len_after, n_popped);
     }
-    if (a.R.nstep > 1) a.S.nstep_len[e] = len_after;
+  } else if (shaping && a.R.reduce_rewards) {
+    a.IO.agent_reward[e] = rsum;
+    shaper_add(a, e, 0, 1, rsum, done, len_before, len_after, n_popped);
+  }
+  if (shaping) {
+    if (a.R.nstep > 1) S.nstep_len[e] = len_after;
     a.IO.n_popped[e] = n_popped;
   }
 }
 
-// host side: is every asset part of an OUPair laid out (role0, role1) consecutively?
+// host side: is every asset part of an OUPair laid out (role0, role1) with in-order noise slots?
 static inline bool all_ou_pairs(const MdgParams& P) {
   if (P.n_assets % 2) return false;
   for (int i = 0; i < P.n_assets; i += 2) {
     const MdgAssetGen &g0 = P.gen[i], &g1 = P.gen[i + 1];
+    const int s = 3 * (i / 2);
     if (g0.type != MDG_GEN_OUPAIR || g1.type != MDG_GEN_OUPAIR || g0.role != 0 || g1.role != 1 ||
-        g1.partner != i || g0.gslot < 0)
+        g1.partner != i || g0.gslot < 0 || g0.nslot_aux != s || g0.nslot != s + 1 || g1.nslot != s + 2)
       return false;
   }
-  return true;
+  return P.n_normals == 3 * (P.n_assets / 2);
 }
 
-template <int CAP>
-static inline int launch_step(const StepArgs& a, bool exact) {
+static inline int launch_step(const StepArgs& a) {
   const int64_t N = a.L.n_envs;
   const unsigned grid = (unsigned)((N + kBlock - 1) / kBlock);
-  cudaStream_t st = (cudaStream_t)a.L.stream;
-  constexpr size_t smem = step_smem_bytes<CAP>();
-  static bool attr_done = false;  // opt in to > 48 KB dynamic shared memory once per process
-  if (!attr_done) {
-    cudaError_t ce = cudaSuccess;
-    if constexpr (CAP % 2 == 0)
-      ce = cudaFuncSetAttribute(step_kernel<CAP, true, MDG_GEN_OUPAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce == cudaSuccess)
-      ce = cudaFuncSetAttribute(step_kernel<CAP, true, MDG_GEN_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce == cudaSuccess)
-      ce = cudaFuncSetAttribute(step_kernel<CAP, false, MDG_GEN_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return cuda_err(ce, "mdg_step smem attribute");
-    attr_done = true;
-  }
-  if constexpr (CAP % 2 == 0) {
-    if (exact && all_ou_pairs(a.P)) {
-      step_kernel<CAP, true, MDG_GEN_OUPAIRS><<<grid, kBlock, smem, st>>>(a);
-      return cuda_err(cudaGetLastError(), "mdg_step launch");
-    }
-  }
-  if (exact)
-    step_kernel<CAP, true, MDG_GEN_GENERIC><<<grid, kBlock, smem, st>>>(a);
+  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * kBlock;
+  if (all_ou_pairs(a.P))
+    step_kernel<true><<<grid, kBlock, smem, (cudaStream_t)a.L.stream>>>(a);
   else
-    step_kernel<CAP, false, MDG_GEN_GENERIC><<<grid, kBlock, smem, st>>>(a);
+    step_kernel<false><<<grid, kBlock, smem, (cudaStream_t)a.L.stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_step launch");
 }
-
-// one translation unit per capacity (mdg_step_inst.cu, -DMDG_CAP=n) so they compile in parallel
-int launch_step_cap1(const StepArgs& a, bool exact);
-int launch_step_cap2(const StepArgs& a, bool exact);
-int launch_step_cap4(const StepArgs& a, bool exact);
-int launch_step_cap8(const StepArgs& a, bool exact);
-int launch_step_cap16(const StepArgs& a, bool exact);
 
 }  // namespace mdg

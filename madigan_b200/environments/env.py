@@ -119,7 +119,7 @@ class Env:
         self.t = dict(
             price=z((nA, N), **f8), ledger=z((nA, N), **f8), mean_entry=z((nA, N), **f8),
             borrowed=z((nA, N), **f8), cash=z((N,), **f8), gstate=z((max(1, self.P.n_gstate), N), **f8),
-            timestamp=z((N,), dtype=torch.int64, device=dev),
+            timestamp=z((N,), dtype=torch.int64, device=dev), folds=z((5, N), **f8),
             shaper_A=z((self.ra, N), **f8), shaper_B=z((self.ra, N), **f8),
             nstep_ring=z((self.R.nstep, self.ra, N), **f8), nstep_len=z((N,), dtype=torch.int32, device=dev),
             obs_price=z((k, nA, N), **f8), obs_port=z((k, nA + 1, N), **f8),
@@ -133,7 +133,7 @@ class Env:
         )
         S = A.MdgState()
         for name in ("price", "ledger", "mean_entry", "borrowed", "cash", "gstate", "timestamp", "shaper_A",
-                     "shaper_B", "nstep_ring", "nstep_len"):
+                     "shaper_B", "nstep_ring", "nstep_len", "folds"):
             setattr(S, name, self.t[name].data_ptr())
         self._S = S
         IO = A.MdgStepIO()
@@ -310,8 +310,12 @@ class Env:
         return self._d
 
     def invalidate(self):
-        """Call after writing into a live state view (e.g. ``env.currentPrices[:, 1] = 4``)."""
+        """Call after writing into a live state view (e.g. ``env.currentPrices[:, 1] = 4``): drops the
+        cached derived accounting and recomputes the portfolio folds the step kernel carries in state."""
         self._version += 1
+        with torch.cuda.device(self.device):
+            check(self._lib.mdg_refresh_folds(C.byref(self.P), C.byref(self._S), C.byref(self._launch())))
+        self.launches += 1
 
     # live views of state (reference: return_value_policy::reference, env.cpp:897-913)
     @property
@@ -464,4 +468,4 @@ class Env:
         m = sd["_meta"]
         self.head, self.n_valid, self._gstep = m["head"], m["n_valid"], m["gstep"]
         self.seed, self.env_offset = m["seed"], m["env_offset"]
-        self._version += 1
+        self.invalidate()

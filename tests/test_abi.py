@@ -50,6 +50,7 @@ def test_argument_validation_without_gpu(cdll):
     P, _ = make_params("OU")
     L = A.MdgLaunch(n_envs=4, window=8, head=9)  # head outside the ring
     S, IO = A.MdgState(), A.MdgStepIO()
+    S.folds = 1  # non-null dummies; never dereferenced because validation fails first
     with pytest.raises(ValueError):
         check(cdll.mdg_step(C.byref(P), None, C.byref(S), C.byref(IO), C.byref(L)))
     L = A.MdgLaunch(n_envs=4, window=8, head=0, mode=A.MODE_SINGLE, asset_idx=7)
