@@ -142,6 +142,22 @@ static __device__ __noinline__ double draw_uniform(LazyDraws& c, int slot) {
   return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
 }
 
+// Draw source of the reset kernel's recurrence phase: this (env, tick)'s normals were generated into
+// shared memory by all lanes of the block beforehand; uniforms (trend generators only) stay on demand.
+struct TickDraws {
+  const double* z;         // z[slot]
+  const double* uniforms;  // [n_uniforms][N] for this tick (validation mode) or nullptr
+  int64_t N, e;
+  uint32_t gid, k0, k1, t_lo, t_hi;
+};
+__device__ __forceinline__ double draw_normal(TickDraws& c, int slot) { return c.z[slot]; }
+static __device__ __noinline__ double draw_uniform(TickDraws& c, int slot) {
+  if (c.uniforms) return c.uniforms[(int64_t)slot * c.N + c.e];
+  uint64_t x0, x1;
+  philox4x32_10(c.gid, (1u << 16) | (uint32_t)(slot >> 1), c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
+  return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
+}
+
 // ---------------------------------------------------------------------------
 // generator state flags (bit0 trending, bit1 direction +1, bits 32.. remaining length)
 // ---------------------------------------------------------------------------

@@ -323,7 +323,8 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
       A.rML += n_ml - o_ml;
       A.rBM += bm - o_bm;
       A.rSE += ((cur < 0.) ? n_ml : 0.) - o_se;
-      A.G += fabs(n_av) + fabs(n_ml) + fabs(bm) + fabs(amount) + fabs(transactionCost) + fabs(o_bm);
+      // every new term's magnitude is at most its old magnitude (already in G) plus |units|*(|price|+|tp|)
+      A.G += 3. * (fabs(tu) * (fabs(price) + fabs(transactionPrice))) + fabs(transactionCost);
     } else if (risk != MDG_RISK_INSUFF_MARGIN) {
       A.bad_risk = true;
     }

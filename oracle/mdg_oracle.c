@@ -599,6 +599,12 @@ static void shaper_add(OrcEnv *e, const double *raw, int ra, const double *port,
     while (e->ring_len > 0) shaper_pop(e, ra, out);
 }
 
+/* test hook: feed one (raw reward vector, next_state.portfolio[-1], done) to the n-step shaper */
+void orc_shaper_feed(OrcEnv *e, const double *raw, int ra, const double *port, int done, OrcStepOut *out) {
+  memset(out, 0, sizeof(*out));
+  shaper_add(e, raw, ra, port, done, out);
+}
+
 /* ------------------------------------------------------------------ */
 /* Env  (environments/cpp/Env.h)                                        */
 /* ------------------------------------------------------------------ */

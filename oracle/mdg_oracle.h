@@ -66,6 +66,7 @@ void orc_tick(OrcEnv *e, const double *normals, const double *uniforms);
 void orc_reset(OrcEnv *e, const double *normals, const double *uniforms, OrcStepOut *out);
 void orc_step(OrcEnv *e, int mode, const double *units, int asset_idx, const double *normals,
               const double *uniforms, OrcStepOut *out);
+void orc_shaper_feed(OrcEnv *e, const double *raw, int ra, const double *port, int done, OrcStepOut *out);
 /* Portfolio primitives, exposed for the reference's ledger known-answer tests */
 int orc_check_risk(const OrcEnv *e);
 int orc_check_risk_asset(const OrcEnv *e, int i, double units);

@@ -72,6 +72,8 @@ def lib():
         L.orc_reset.restype = None
         L.orc_step.argtypes = [pe, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(OrcStepOut)]
         L.orc_step.restype = None
+        L.orc_shaper_feed.argtypes = [pe, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(OrcStepOut)]
+        L.orc_shaper_feed.restype = None
         L.orc_check_risk.argtypes = [pe]
         L.orc_check_risk.restype = C.c_int
         L.orc_check_risk_asset.argtypes = [pe, C.c_int, dbl]
@@ -164,6 +166,15 @@ class OracleEnv:
             mode, un, ai = A.MODE_MULTI, np.ascontiguousarray(units, dtype=np.float64), 0
         self.L.orc_step(C.byref(self.e), mode, _ptr(un), ai, _ptr(n), _ptr(u), C.byref(o))
         return self._out(o)
+
+    def shaper_feed(self, raw, port, done):
+        """Feed one raw reward vector to the n-step shaper; returns (popped rewards (n_popped, ra), n_popped)."""
+        raw = np.ascontiguousarray(raw, dtype=np.float64)
+        port = np.ascontiguousarray(port, dtype=np.float64)
+        o = OrcStepOut()
+        self.L.orc_shaper_feed(C.byref(self.e), _ptr(raw), len(raw), _ptr(port), int(done), C.byref(o))
+        ra = len(raw)
+        return np.array([list(o.shaped[k][:ra]) for k in range(o.n_popped)]).reshape(o.n_popped, ra), o.n_popped
 
     # -- Portfolio / Broker primitives
     def handleTransaction(self, i, price, units, cost=0.):

@@ -1,0 +1,114 @@
+"""GPU: the window materialiser (StackerDiscrete.current_data + the six normalisers) against
+(a) vectors produced by the reference's own preprocessor (tests/golden/preprocessor.npz) and
+(b) the numpy restatement on random rings, all layouts and dtypes.  Bar: 1e-9 relative in fp64;
+fp32 output is the fp64 result rounded once (checked to 1e-6)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import py_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NORMS = [None, "lookback", "lookback_log", "log", "standard_normal", "log_standard_normal", "expanding"]
+
+
+def make_env(n_envs, n_assets, window):
+    from madigan_b200.environments import Env
+    cfg = {"data_source_config": {"mean": [10.] * n_assets, "theta": [.1] * n_assets, "phi": [.02] * n_assets}}
+    return Env("OU", 1e6, cfg, n_envs=n_envs, window=window, seed=3)
+
+
+def load_ring(env, rows, newest_index):
+    """rows: (R, nF, N) price rows with global indices 0..R-1; ring slot = index % k."""
+    k = env.k
+    R = rows.shape[0]
+    for r in range(max(0, R - k), R):
+        env.t["obs_price"][r % k].copy_(torch.from_numpy(np.ascontiguousarray(rows[r])))
+    env.head = newest_index % k
+    env.n_valid = min(k, R)
+
+
+@pytest.mark.parametrize("norm", NORMS)
+def test_window_matches_reference_preprocessor(norm):
+    PP = np.load(os.path.join(GOLD, "preprocessor.npz"))
+    prices, steps, lens = PP["prices"], PP["steps"], PP["lens"]
+    ref = PP[f"out_{norm}"]
+    k, nF = ref.shape[1], ref.shape[2]
+    env = make_env(7, nF, k)
+    for idx, (t, ln) in enumerate(zip(steps, lens)):
+        rows = np.repeat(prices[:t + 1, :, None], 7, axis=2)
+        load_ring(env, rows, t)
+        got = env.window(norm, dtype=torch.float64).cpu().numpy()
+        assert got.shape == (7, ln, nF)
+        for e in range(7):
+            np.testing.assert_allclose(got[e], ref[idx, :ln], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("norm", NORMS)
+@pytest.mark.parametrize("nF,k,N", [(1, 64, 1000), (2, 64, 333), (16, 64, 300), (5, 10, 65), (16, 7, 33)])
+def test_window_matches_numpy_random(norm, nF, k, N):
+    rng = np.random.default_rng(nF * 100 + k)
+    env = make_env(N, nF, k)
+    R = k + 11
+    rows = np.abs(10 + np.cumsum(rng.standard_normal((R, nF, N)) * .2, axis=0)) + .1
+    rows[:, 0, 0] = 3.0  # constant series -> std 0
+    load_ring(env, rows, R - 1)
+    ref = py_oracle.normalise_batch(rows[R - k:].transpose(2, 0, 1), norm)  # (N,k,nF)
+    got = env.window(norm, dtype=torch.float64).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-11, equal_nan=True)
+    got_cf = env.window(norm, dtype=torch.float64, channels_first=True).cpu().numpy()
+    np.testing.assert_allclose(got_cf, ref.transpose(0, 2, 1), rtol=1e-9, atol=1e-11, equal_nan=True)
+    got32 = env.window(norm, dtype=torch.float32).cpu().numpy()
+    np.testing.assert_allclose(got32, ref.astype(np.float32), rtol=2e-6, atol=1e-6, equal_nan=True)
+    # partially filled window (fewer rows than k), oldest first
+    nv = max(1, k // 3)
+    ref_p = py_oracle.normalise_batch(rows[R - nv:].transpose(2, 0, 1), norm)
+    got_p = env.window(norm, dtype=torch.float64, n_valid=nv).cpu().numpy()
+    np.testing.assert_allclose(got_p, ref_p, rtol=1e-9, atol=1e-11, equal_nan=True)
+
+
+def test_stacker_discrete_api_roundtrip():
+    """The reference's agent loop (offpolicy_q.py:93-99): reset -> stream_state -> initialize_history -> current_data."""
+    from madigan_b200.environments import Env
+    from madigan_b200.utils.preprocessor import StackerDiscrete
+    from madigan_b200.environments.data_source import make_params
+    from oracle.oracle import OracleBatch
+    cfg = {"data_source_config": {"theta": .015, "phi": .01, "noise": .03}}
+    N, k = 50, 12
+    env = Env("OUPair", 1e6, cfg, n_envs=N, window=k, seed=5)
+    env.setRequiredMargin(1.)
+    P, _ = make_params("OUPair", cfg["data_source_config"], required_margin=1.)
+    orc = OracleBatch(N, P, None, window=k, seed=5)
+    pre = StackerDiscrete(k, env.nFeats, norm=True, norm_type="lookback")
+    rng = np.random.default_rng(0)
+    nz = rng.standard_normal((1, 3, N))
+    state = env.reset(normals=nz)
+    orc.reset(fill_ticks=1, normals=nz)
+    pre.reset_state()
+    pre.stream_state(state)
+    assert len(pre) == 1
+    # initialize_history: k-1 no-action steps (here with an injected stream so both sides agree exactly)
+    while len(pre) < k:
+        nz = rng.standard_normal((3, N))
+        s, r, d, info = env.step(normals=nz)
+        orc.step(None, normals=nz)
+        pre.stream_state(s)
+    cd = pre.current_data()
+    ref = py_oracle.normalise_batch(orc.window(), "lookback")
+    np.testing.assert_allclose(cd.price.cpu().numpy(), ref, rtol=1e-9)
+    assert cd.portfolio.shape == (N, k, 3) and cd.timestamp.shape == (N, k)
+    np.testing.assert_array_equal(cd.timestamp.cpu().numpy(), np.tile(np.arange(2, k + 2), (N, 1)))
+    np.testing.assert_allclose(cd.portfolio.cpu().numpy()[:, :, 0], 1.0)
+    # one real step: the window slides by one row
+    u = rng.integers(-1, 2, size=(N, 2)) * 1000.
+    nz = rng.standard_normal((3, N))
+    s, r, d, info = env.step(torch.from_numpy(u), normals=nz)
+    orc.step(u, normals=nz)
+    pre.stream_state(s)
+    cd = pre.current_data()
+    np.testing.assert_allclose(cd.price.cpu().numpy(), py_oracle.normalise_batch(orc.window(), "lookback"), rtol=1e-9)
+    last_port = cd.portfolio[:, -1].cpu().numpy()
+    np.testing.assert_allclose(last_port, orc.obs_port[orc.head].T, rtol=1e-9, atol=1e-12)
