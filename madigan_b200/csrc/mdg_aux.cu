@@ -95,6 +95,39 @@ __device__ __forceinline__ double nan_to_num(double x) {  // np.nan_to_num
   return x;
 }
 
+// Sum over the time axis of one column, in numpy's order (the reference's mean/std are numpy reductions):
+// a (k, F>1) array reduced over axis 0 accumulates row by row -> a left-to-right fold; a (k, 1) array is
+// coalesced to 1-D and summed with numpy's pairwise scheme (8 interleaved accumulators for n <= 128).
+// MODE 0: x   1: (x-c)^2   2: x with NaN -> 0 (nansum)   3: (x-c)^2 with NaN -> 0
+template <int MODE>
+__device__ __forceinline__ double col_term(const double* col, int s, int sstride, double c) {
+  const double x = col[s * sstride];
+  if (MODE == 0) return x;
+  if (MODE == 2) return (x == x) ? x : 0.;
+  const double d = x - c;
+  if (MODE == 3 && !(x == x)) return 0.;
+  return d * d;
+}
+template <int MODE>
+__device__ __forceinline__ double col_sum(const double* col, int n, int sstride, double c, bool pairwise) {
+  if (!pairwise || n < 8 || n > 128) {
+    double s = col_term<MODE>(col, 0, sstride, c);
+    for (int i = 1; i < n; ++i) s = s + col_term<MODE>(col, i, sstride, c);
+    return s;
+  }
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = col_term<MODE>(col, j, sstride, c);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = r[j] + col_term<MODE>(col, i + j, sstride, c);
+  }
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; ++i) res = res + col_term<MODE>(col, i, sstride, c);
+  return res;
+}
+
 struct WindowArgs {
   const double* ring;  // [k][F][N]
   void* out;
@@ -147,34 +180,22 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
         }
         break;
       case MDG_NORM_STANDARD: {  // nan_to_num((x - mean(0)) / std(0))
-        double sum = col[0];
-        for (int s = 1; s < nv; ++s) sum = sum + col[s * a.sstride];
-        const double mean = sum / nv;
-        double ss = 0.;
-        for (int s = 0; s < nv; ++s) {
-          const double d = col[s * a.sstride] - mean;
-          ss = (s == 0) ? d * d : ss + d * d;
-        }
-        const double sd = sqrt(ss / nv);
+        const bool pw = (F == 1);
+        const double mean = col_sum<0>(col, nv, a.sstride, 0., pw) / nv;
+        const double sd = sqrt(col_sum<1>(col, nv, a.sstride, mean, pw) / nv);
         for (int s = 0; s < nv; ++s) col[s * a.sstride] = nan_to_num((col[s * a.sstride] - mean) / sd);
         break;
       }
       case MDG_NORM_LOG_STANDARD: {  // x = log(x); nan_to_num((x - nanmean) / nanstd)
-        double sum = 0.;
+        const bool pw = (F == 1);
         int cnt = 0;
         for (int s = 0; s < nv; ++s) {
           const double x = log(col[s * a.sstride]);
           col[s * a.sstride] = x;
-          if (x == x) { sum = (cnt == 0) ? x : sum + x; ++cnt; }
+          if (x == x) ++cnt;
         }
-        const double mean = sum / cnt;
-        double ss = 0.;
-        int c2 = 0;
-        for (int s = 0; s < nv; ++s) {
-          const double x = col[s * a.sstride];
-          if (x == x) { const double d = x - mean; ss = (c2 == 0) ? d * d : ss + d * d; ++c2; }
-        }
-        const double sd = sqrt(ss / cnt);
+        const double mean = col_sum<2>(col, nv, a.sstride, 0., pw) / cnt;
+        const double sd = sqrt(col_sum<3>(col, nv, a.sstride, mean, pw) / cnt);
         for (int s = 0; s < nv; ++s) col[s * a.sstride] = nan_to_num((col[s * a.sstride] - mean) / sd);
         break;
       }

@@ -54,7 +54,7 @@ def test_window_matches_numpy_random(norm, nF, k, N):
     env = make_env(N, nF, k)
     R = k + 11
     rows = np.abs(10 + np.cumsum(rng.standard_normal((R, nF, N)) * .2, axis=0)) + .1
-    rows[:, 0, 0] = 3.0  # constant series -> std 0
+    rows[:, 0, 0] = 3.0  # constant series -> std 0: the result hinges on numpy's summation order, which the kernel follows
     load_ring(env, rows, R - 1)
     ref = py_oracle.normalise_batch(rows[R - k:].transpose(2, 0, 1), norm)  # (N,k,nF)
     got = env.window(norm, dtype=torch.float64).cpu().numpy()
@@ -112,3 +112,4 @@ def test_stacker_discrete_api_roundtrip():
     np.testing.assert_allclose(cd.price.cpu().numpy(), py_oracle.normalise_batch(orc.window(), "lookback"), rtol=1e-9)
     last_port = cd.portfolio[:, -1].cpu().numpy()
     np.testing.assert_allclose(last_port, orc.obs_port[orc.head].T, rtol=1e-9, atol=1e-12)
+
