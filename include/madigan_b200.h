@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 4
+#define MDG_ABI_VERSION 6
 #define MDG_MAX_ASSETS 16
 #define MDG_GEN_NPARAM 10
 #define MDG_MAX_NSTEP 64
@@ -141,6 +141,9 @@ typedef struct MdgState {
   double *shaper_B;   /* [ra][N] DSR/DDR moving second moment (nullable)   */
   double *nstep_ring; /* [nstep][ra][N] raw rewards waiting in the n-step buffer (nullable when nstep==1) */
   int32_t *nstep_len; /* [N] entries currently in the n-step buffer          (nullable when nstep==1) */
+  int64_t *reset_ts;  /* [N] timestamp at the end of the env's last reset: window rows older than that come
+                         from MdgStepIO.pre_price (portfolio rows: flat [1,0,...,0]); the timestamp of a
+                         window row is timestamp - age (every ring/prefix row is exactly one generator tick) */
   double *folds;      /* [5][N] cache of the portfolio's left-to-right folds at the current prices:
                          assetValue, meanEntry.ledger, sum borrowedMargin, short entry value, and a
                          magnitude bound.  Written by mdg_step / mdg_reset / mdg_init_state; call
@@ -154,7 +157,11 @@ typedef struct MdgStepIO {
   const double *uniforms; /* nullable. validation mode: [ticks][n_uniforms][N] uniforms in [0,1) */
   double *obs_price;      /* ring [k][nA][N]   State.price rows      */
   double *obs_port;       /* ring [k][nA+1][N] State.portfolio rows (ledgerNormedFull) */
-  int64_t *obs_time;      /* ring [k][N]       State.timestamp rows  */
+  double *pre_price;      /* [N][k][nA] price rows of the last reset's history fill, env-major: a reset
+                             rewrites an env's whole window, and k*nA scattered 8-byte writes into the
+                             env-minor ring cost 8x their size in HBM traffic (sector read-modify-write),
+                             so those rows live here, contiguous per env; row k-1 is the newest.  The ring
+                             keeps only rows written by steps (and the newest row, = current state). */
   double *reward;         /* [N]  Env::step reward (log equity return, clamped) */
   uint8_t *done;          /* [N]                                       */
   double *trans_price;    /* [nA][N] BrokerResponse.transactionPrice   */
@@ -233,6 +240,15 @@ int mdg_step(const MdgParams *params, const MdgReward *reward, const MdgState *s
 int mdg_reset(const MdgParams *params, const MdgState *state, const MdgStepIO *io,
               const MdgLaunch *launch, const uint8_t *mask, int fill_ticks, int clear_nstep);
 
+/* Same operation with a caller-provided device workspace (at least mdg_reset_workspace_bytes): the
+ * resetting envs are compacted into a list, their noise is generated by one perfectly packed kernel
+ * and the serial recurrences by another -- several times faster when a few percent of the envs reset
+ * every step.  workspace == NULL falls back to mdg_reset.  The workspace holds no state between calls. */
+int mdg_reset_ws(const MdgParams *params, const MdgState *state, const MdgStepIO *io,
+                 const MdgLaunch *launch, const uint8_t *mask, int fill_ticks, int clear_nstep,
+                 void *workspace, int64_t workspace_bytes);
+int64_t mdg_reset_workspace_bytes(const MdgParams *params, int64_t n_envs, int fill_ticks);
+
 /* Constructor state (Env.h:139-165 before the first tick): generator start values,
  * empty ledger, cash=init_cash, timestamp=0, shaper state zero. */
 int mdg_init_state(const MdgParams *params, const MdgReward *reward, const MdgState *state,
@@ -247,13 +263,23 @@ int mdg_derived(const MdgParams *params, const MdgState *state, const MdgDerived
 
 /* StackerDiscrete.current_data price window (preprocessor.py:183-189) with the
  * normalisers of preprocessor.py:53-107: ring [k][F][N] -> out (N,k,F) or (N,F,k).
- * n_valid = rows currently in the ring (<= k), oldest first. */
-int mdg_materialise_window(const double *ring, int64_t n_envs, int32_t n_feats, int32_t window,
-                           int32_t head, int32_t n_valid, int32_t norm_type, void *out,
-                           int32_t out_dtype, int32_t out_layout, void *stream);
-/* int64 timestamps ring [k][N] -> (N, n_valid) */
-int mdg_materialise_time(const int64_t *ring, int64_t n_envs, int32_t window, int32_t head,
-                         int32_t n_valid, int64_t *out, void *stream);
+ * n_valid = rows currently in the window (<= k), oldest first. */
+typedef struct MdgWindow {
+  const double *ring;        /* [k][F][N] obs_price or obs_port                               */
+  const double *prefix;      /* [N][k][F] pre_price, or NULL                                   */
+  const int64_t *timestamp;  /* [N] MdgState.timestamp (NULL: every row comes from the ring)   */
+  const int64_t *reset_ts;   /* [N] MdgState.reset_ts                                          */
+  int64_t n_envs;
+  int32_t n_feats, window, head, n_valid;
+  int32_t norm_type;         /* MDG_NORM_*                                                     */
+  int32_t flat_prefix;       /* prefix==NULL and rows older than the reset are [1,0,...,0]     */
+  int32_t out_dtype, out_layout;
+  void *out;
+  void *stream;
+} MdgWindow;
+int mdg_materialise_window(const MdgWindow *w);
+/* (N, n_valid) int64 timestamps of the window rows: timestamp[e] - (n_valid-1-s) */
+int mdg_materialise_time(const int64_t *timestamp, int64_t n_envs, int32_t n_valid, int64_t *out, void *stream);
 
 /* Reduce the slab to MDG_STATS_NSCALAR + 2*nA doubles (per-asset sum |position value|/equity
  * and count of non-flat positions): the vector that is all-reduced across GPUs. */

@@ -5,7 +5,7 @@ checks the struct sizes against the compiled library (``mdg_sizeof``).
 """
 import ctypes as C
 
-MDG_ABI_VERSION = 4
+MDG_ABI_VERSION = 6
 MDG_MAX_ASSETS = 16
 MDG_GEN_NPARAM = 10
 MDG_MAX_NSTEP = 64
@@ -58,12 +58,12 @@ class MdgReward(C.Structure):
 
 class MdgState(C.Structure):
     _fields_ = [(n, _dp) for n in ("price", "ledger", "mean_entry", "borrowed", "cash", "gstate",
-                                   "timestamp", "shaper_A", "shaper_B", "nstep_ring", "nstep_len", "folds")]
+                                   "timestamp", "shaper_A", "shaper_B", "nstep_ring", "nstep_len", "reset_ts", "folds")]
 
 
 class MdgStepIO(C.Structure):
     _fields_ = [(n, _dp) for n in ("units", "normals", "uniforms", "obs_price", "obs_port",
-                                   "obs_time", "reward", "done", "trans_price", "trans_units",
+                                   "pre_price", "reward", "done", "trans_price", "trans_units",
                                    "trans_cost", "risk", "margin_call", "agent_reward",
                                    "shaped_reward", "n_popped")]
 
@@ -73,6 +73,13 @@ class MdgLaunch(C.Structure):
                 ("window", C.c_int32), ("head", C.c_int32), ("mode", C.c_int32),
                 ("asset_idx", C.c_int32), ("nstep_pos", C.c_int32), ("_pad", C.c_int32),
                 ("stream", C.c_void_p)]
+
+
+class MdgWindow(C.Structure):
+    _fields_ = [("ring", _dp), ("prefix", _dp), ("timestamp", _dp), ("reset_ts", _dp), ("n_envs", C.c_int64),
+                ("n_feats", C.c_int32), ("window", C.c_int32), ("head", C.c_int32), ("n_valid", C.c_int32),
+                ("norm_type", C.c_int32), ("flat_prefix", C.c_int32), ("out_dtype", C.c_int32),
+                ("out_layout", C.c_int32), ("out", _dp), ("stream", _dp)]
 
 
 class MdgDerived(C.Structure):
@@ -92,14 +99,14 @@ SYMBOLS = {
     "mdg_step": (C.c_int, [_P(MdgParams), _P(MdgReward), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch)]),
     "mdg_reset": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch), C.c_void_p,
                             C.c_int, C.c_int]),
+    "mdg_reset_ws": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch), C.c_void_p,
+                               C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "mdg_reset_workspace_bytes": (C.c_int64, [_P(MdgParams), C.c_int64, C.c_int]),
     "mdg_init_state": (C.c_int, [_P(MdgParams), _P(MdgReward), _P(MdgState), _P(MdgLaunch)]),
     "mdg_refresh_folds": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgLaunch)]),
     "mdg_derived": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgDerived), _P(MdgLaunch)]),
-    "mdg_materialise_window": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                         C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
-                                         C.c_void_p]),
-    "mdg_materialise_time": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                       C.c_void_p, C.c_void_p]),
+    "mdg_materialise_window": (C.c_int, [_P(MdgWindow)]),
+    "mdg_materialise_time": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "mdg_episode_stats": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch),
                                     C.c_void_p]),
 }
@@ -114,4 +121,4 @@ def bind(lib):
     return lib
 
 
-STRUCTS = (MdgAssetGen, MdgParams, MdgReward, MdgState, MdgStepIO, MdgLaunch, MdgDerived)  # mdg_sizeof order
+STRUCTS = (MdgAssetGen, MdgParams, MdgReward, MdgState, MdgStepIO, MdgLaunch, MdgDerived, MdgWindow)  # mdg_sizeof order

@@ -78,12 +78,8 @@ __global__ void __launch_bounds__(kResetBlock) reset_kernel(const __grid_constan
     const long long ts = a.S.timestamp[e];
     s_ts[it] = ts;
     a.S.timestamp[e] = ts + fill;
-    for (int t = 0; t < fill; ++t) {
-      int slot = (a.L.head - (fill - 1 - t)) % k;
-      if (slot < 0) slot += k;
-      a.IO.obs_port[((int64_t)slot * (na + 1)) * N + e] = (cash - 0.) / eq;
-      a.IO.obs_time[(int64_t)slot * N + e] = ts + t + 1;
-    }
+    a.S.reset_ts[e] = ts + fill;
+    a.IO.obs_port[((int64_t)a.L.head * (na + 1)) * N + e] = (cash - 0.) / eq;  // newest row = current state
   }
   __syncthreads();
   // (b) items ordered leader-major so that neighbouring lanes run the same generator type
@@ -103,7 +99,7 @@ __global__ void __launch_bounds__(kResetBlock) reset_kernel(const __grid_constan
       a.S.borrowed[(int64_t)(i0 + c) * N + e] = 0.;
     }
     LazyDraws dr;
-    dr.N = N; dr.e = e;
+    dr.N = N; dr.e = e; dr.gstride = N;
     dr.gid = (uint32_t)(a.L.env_offset + e);
     dr.k0 = (uint32_t)a.L.seed; dr.k1 = (uint32_t)(a.L.seed >> 32);
     const long long ts0 = s_ts[d];
@@ -115,18 +111,194 @@ __global__ void __launch_bounds__(kResetBlock) reset_kernel(const __grid_constan
       dr.cached_block = -1;
       dr.normals = a.IO.normals ? a.IO.normals + (int64_t)t * P.n_normals * N : nullptr;
       dr.uniforms = a.IO.uniforms ? a.IO.uniforms + (int64_t)t * P.n_uniforms * N : nullptr;
-      int slot = (a.L.head - (fill - 1 - t)) % k;
-      if (slot < 0) slot += k;
       double pair_mean = 0.;
 #pragma unroll 1
       for (int c = 0; c < cnt; ++c) {
         const MdgAssetGen& g = P.gen[i0 + c];
         double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
         pr[c] = gen_tick(g, pr[c], gs, dr, pair_mean);
-        a.IO.obs_price[((int64_t)slot * na + i0 + c) * N + e] = pr[c];
-        a.IO.obs_port[((int64_t)slot * (na + 1) + i0 + c + 1) * N + e] = (0. * pr[c]) / eq;
+        a.IO.pre_price[((int64_t)e * k + (k - fill + t)) * na + i0 + c] = pr[c];
+        if (t == fill - 1) {  // newest row = current state, also in the ring
+          a.IO.obs_price[((int64_t)a.L.head * na + i0 + c) * N + e] = pr[c];
+          a.IO.obs_port[((int64_t)a.L.head * (na + 1) + i0 + c + 1) * N + e] = (0. * pr[c]) / eq;
+        }
       }
     }
+    for (int c = 0; c < cnt; ++c) a.S.price[(int64_t)(i0 + c) * N + e] = pr[c];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// reset with a workspace: three packed kernels instead of one block-local kernel.
+//   scan : one thread per env; flagged envs append themselves to a global list (warp-aggregated
+//          atomics), get a fresh portfolio and DataSource::reset().
+//   rng  : one thread per (listed env, tick, Philox block) -> the expensive, dependence-free part
+//          (Philox + Box-Muller) runs perfectly packed at full occupancy, however scattered the
+//          resetting envs are; normals go to an L2-resident scratch [listed env][tick][slot].
+//   recur: one thread per (listed env, generator group): the serial recurrence over the ticks with
+//          the generator state in registers / local memory, reading the scratch, writing ring rows.
+// The host launches ceil(N / cap) rng+recur passes without knowing how many envs reset; passes beyond
+// the list end exit at once.
+// ---------------------------------------------------------------------------
+struct ResetWsArgs {
+  MdgParams P;
+  MdgState S;
+  MdgStepIO IO;
+  MdgLaunch L;
+  const uint8_t* mask;
+  int fill_ticks;
+  int clear_nstep;
+  int* count;       // workspace: number of listed envs
+  int* list;        // workspace: env index of each listed env
+  double* scratch;  // workspace: [cap][fill_ticks][n_normals]
+  int cap;          // listed envs per pass
+  int pass;
+};
+
+__global__ void __launch_bounds__(256) reset_scan_kernel(const __grid_constant__ ResetWsArgs a) {
+  const MdgParams& P = a.P;
+  const int64_t N = a.L.n_envs;
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool flag = (e < N) && (!a.mask || a.mask[e]);
+  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+  if (!ballot) return;
+  int base = 0;
+  if (lane == (__ffs(ballot) - 1)) base = atomicAdd(a.count, __popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+  if (!flag) return;
+  a.list[base + __popc(ballot & ((1u << lane) - 1u))] = (int)e;
+  const int na = P.n_assets;
+  const int fill = a.fill_ticks;
+  const double cash = P.init_cash;
+  const double eq = cash + 0. - 0.;  // flat portfolio: equity == cash
+  if (a.clear_nstep && a.S.nstep_len) a.S.nstep_len[e] = 0;  // offpolicy_q.py:94
+  a.S.cash[e] = cash;
+  if (a.S.folds) {  // flat portfolio: every fold is a sum of zeros
+    a.S.folds[(int64_t)MDG_FOLD_AV * N + e] = 0.;
+    a.S.folds[(int64_t)MDG_FOLD_ML * N + e] = 0.;
+    a.S.folds[(int64_t)MDG_FOLD_BM * N + e] = 0.;
+    a.S.folds[(int64_t)MDG_FOLD_SE * N + e] = 0.;
+    a.S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(cash);
+  }
+  const long long ts = a.S.timestamp[e];
+  a.S.timestamp[e] = ts + fill;  // the later kernels recover ts as timestamp - fill
+  a.S.reset_ts[e] = ts + fill;
+  a.IO.obs_port[((int64_t)a.L.head * (na + 1)) * N + e] = (cash - 0.) / eq;  // newest row = current state
+  for (int i = 0; i < na; ++i) {  // dataSource_->reset(); fresh Broker/Account/Portfolio (Env.h:150-165)
+    const MdgAssetGen& g = P.gen[i];
+    double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
+    a.S.price[(int64_t)i * N + e] = gen_reset(g, a.S.price[(int64_t)i * N + e], gs, N);
+    a.S.ledger[(int64_t)i * N + e] = 0.;
+    a.S.mean_entry[(int64_t)i * N + e] = 0.;
+    a.S.borrowed[(int64_t)i * N + e] = 0.;
+  }
+}
+
+__global__ void __launch_bounds__(256) reset_rng_kernel(const __grid_constant__ ResetWsArgs a) {
+  const int count = *a.count;
+  const int first = a.pass * a.cap;
+  if (first >= count) return;
+  const int here = (count - first) < a.cap ? (count - first) : a.cap;
+  const int nn = a.P.n_normals, fill = a.fill_ticks;
+  const int64_t N = a.L.n_envs;
+  if (a.IO.normals) {  // validation mode: copy the injected stream [tick][slot][env]
+    const int64_t total = (int64_t)here * fill * nn;
+    for (int64_t item = (int64_t)blockIdx.x * 256 + threadIdx.x; item < total; item += (int64_t)gridDim.x * 256) {
+      const int s = (int)(item % nn);
+      const int64_t r = item / nn;
+      const int t = (int)(r % fill), d = (int)(r / fill);
+      const int64_t e = a.list[first + d];
+      a.scratch[item] = a.IO.normals[((int64_t)t * nn + s) * N + e];
+    }
+    return;
+  }
+  const int nb = (nn + 1) >> 1;
+  const uint32_t k0 = (uint32_t)a.L.seed, k1 = (uint32_t)(a.L.seed >> 32);
+  const int64_t total = (int64_t)here * fill * nb;
+  for (int64_t item = (int64_t)blockIdx.x * 256 + threadIdx.x; item < total; item += (int64_t)gridDim.x * 256) {
+    const int b = (int)(item % nb);
+    const int64_t r = item / nb;
+    const int t = (int)(r % fill), d = (int)(r / fill);
+    const int64_t e = a.list[first + d];
+    const unsigned long long tick = (unsigned long long)(a.S.timestamp[e] - fill + t);
+    uint64_t x0, x1;
+    philox4x32_10((uint32_t)(a.L.env_offset + e), (uint32_t)b, (uint32_t)tick, (uint32_t)(tick >> 32), k0, k1, x0, x1);
+    const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
+    const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
+    const double r2 = sqrt(-2.0 * fast_log_pos(u1));
+    double sn, cs;
+    fast_sincos_2pi(u2, sn, cs);
+    double* z = a.scratch + ((int64_t)d * fill + t) * nn;
+    z[2 * b] = r2 * cs;
+    if (2 * b + 1 < nn) z[2 * b + 1] = r2 * sn;
+  }
+}
+
+__global__ void __launch_bounds__(128) reset_recur_kernel(const __grid_constant__ ResetWsArgs a) {
+  __shared__ int s_leader[MDG_MAX_ASSETS];
+  __shared__ int s_nlead;
+  const MdgParams& P = a.P;
+  const int na = P.n_assets;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int i = 0; i < na; ++i)
+      if (!(P.gen[i].type == MDG_GEN_OUPAIR && P.gen[i].role == 1)) s_leader[n++] = i;
+    s_nlead = n;
+  }
+  __syncthreads();
+  const int count = *a.count;
+  const int first = a.pass * a.cap;
+  if (first >= count) return;
+  const int here = (count - first) < a.cap ? (count - first) : a.cap;
+  const int nlead = s_nlead;
+  const int nn = P.n_normals, fill = a.fill_ticks, k = a.L.window;
+  const int64_t N = a.L.n_envs;
+  const double cash = P.init_cash;
+  const double eq = cash + 0. - 0.;
+  const bool eq_plain = eq > 0. && eq < 1e300;  // then (0*p)/eq == 0*p exactly
+  const int64_t total = (int64_t)here * nlead;
+  // item = d * nlead + l: the groups of one env are neighbouring lanes -> they read one contiguous scratch row
+  for (int64_t item = (int64_t)blockIdx.x * 128 + threadIdx.x; item < total; item += (int64_t)gridDim.x * 128) {
+    const int d = (int)(item / nlead), l = (int)(item - (int64_t)d * nlead);
+    const int64_t e = a.list[first + d];
+    const int i0 = s_leader[l];
+    const int cnt = (P.gen[i0].type == MDG_GEN_OUPAIR) ? 2 : 1;
+    // generator state of this group in registers / local memory for the whole fast-forward
+    double pr[2], gsl[4];
+    const int gslot0 = P.gen[i0].gslot;
+    const int ngs = gslot0 < 0 ? 0
+                    : (P.gen[i0].type == MDG_GEN_TRENDYOU ? 4 : P.gen[i0].type == MDG_GEN_TRENDOU ? 3
+                       : P.gen[i0].type == MDG_GEN_SIMPLETREND ? 2 : 1);
+    for (int r = 0; r < ngs; ++r) gsl[r] = a.S.gstate[(int64_t)(gslot0 + r) * N + e];
+    for (int c = 0; c < cnt; ++c) pr[c] = a.S.price[(int64_t)(i0 + c) * N + e];
+    TickDraws dr;
+    dr.N = N; dr.e = e; dr.gstride = 1;
+    dr.gid = (uint32_t)(a.L.env_offset + e);
+    dr.k0 = (uint32_t)a.L.seed; dr.k1 = (uint32_t)(a.L.seed >> 32);
+    const long long ts0 = a.S.timestamp[e] - fill;
+    const double* zrow = a.scratch + (int64_t)d * fill * nn;
+#pragma unroll 1
+    for (int t = 0; t < fill; ++t) {
+      const long long tick = ts0 + t;
+      dr.t_lo = (uint32_t)(unsigned long long)tick;
+      dr.t_hi = (uint32_t)((unsigned long long)tick >> 32);
+      dr.z = zrow + (int64_t)t * nn;
+      dr.uniforms = a.IO.uniforms ? a.IO.uniforms + (int64_t)t * P.n_uniforms * N : nullptr;
+      double pair_mean = 0.;
+#pragma unroll 1
+      for (int c = 0; c < cnt; ++c) {
+        const MdgAssetGen& g = P.gen[i0 + c];
+        pr[c] = gen_tick(g, pr[c], gsl, dr, pair_mean);  // role 1 of a pair has no rows of its own (pair_mean)
+        // env-major history row: the groups of one env (neighbouring lanes) fill one contiguous nA*8-byte run
+        a.IO.pre_price[((int64_t)e * k + (k - fill + t)) * na + i0 + c] = pr[c];
+      }
+    }
+    for (int c = 0; c < cnt; ++c) {  // newest row = current state, also in the ring
+      a.IO.obs_price[((int64_t)a.L.head * na + i0 + c) * N + e] = pr[c];
+      a.IO.obs_port[((int64_t)a.L.head * (na + 1) + i0 + c + 1) * N + e] = eq_plain ? 0. * pr[c] : (0. * pr[c]) / eq;
+    }
+    for (int r = 0; r < ngs; ++r) a.S.gstate[(int64_t)(gslot0 + r) * N + e] = gsl[r];
     for (int c = 0; c < cnt; ++c) a.S.price[(int64_t)(i0 + c) * N + e] = pr[c];
   }
 }
@@ -153,6 +325,7 @@ __global__ void __launch_bounds__(kBlock) init_kernel(const __grid_constant__ In
   }
   a.S.cash[e] = a.P.init_cash;
   a.S.timestamp[e] = 0;
+  if (a.S.reset_ts) a.S.reset_ts[e] = 0;
   if (a.S.folds) {
     for (int r = 0; r < 4; ++r) a.S.folds[(int64_t)r * N + e] = 0.;
     a.S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(a.P.init_cash);
@@ -243,6 +416,7 @@ extern "C" int mdg_reset(const MdgParams* P, const MdgState* S, const MdgStepIO*
   int rc = check_common(P, L);
   if (rc) return rc;
   if (!S || !IO) return set_err(MDG_E_INVALID, "null state/io");
+  if (!S->reset_ts || !IO->pre_price) return set_err(MDG_E_INVALID, "state.reset_ts / io.pre_price is null");
   if (L->window < 1 || L->head < 0 || L->head >= L->window) return set_err(MDG_E_INVALID, "bad window/head");
   if (fill_ticks < 1) fill_ticks = 1;
   if (fill_ticks > L->window) return set_err(MDG_E_INVALID, "fill_ticks > window");
@@ -253,6 +427,60 @@ extern "C" int mdg_reset(const MdgParams* P, const MdgState* S, const MdgStepIO*
   const unsigned grid = (unsigned)((L->n_envs + kResetBlock - 1) / kResetBlock);
   reset_kernel<<<grid, kResetBlock, 0, (cudaStream_t)L->stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_reset launch");
+}
+
+extern "C" int64_t mdg_reset_workspace_bytes(const MdgParams* P, int64_t n_envs, int fill_ticks) {
+  if (!P || n_envs < 0) return -1;
+  if (fill_ticks < 1) fill_ticks = 1;
+  // header (count) + list + scratch for min(N, 32768) listed envs per pass
+  const int64_t cap = n_envs < 32768 ? n_envs : 32768;
+  return 256 + 4 * ((n_envs + 63) / 64 * 64) + 8 * cap * (int64_t)fill_ticks * (P->n_normals > 0 ? P->n_normals : 1);
+}
+
+extern "C" int mdg_reset_ws(const MdgParams* P, const MdgState* S, const MdgStepIO* IO, const MdgLaunch* L,
+                            const uint8_t* mask, int fill_ticks, int clear_nstep, void* workspace,
+                            int64_t workspace_bytes) {
+  if (!workspace) return mdg_reset(P, S, IO, L, mask, fill_ticks, clear_nstep);
+  int rc = check_common(P, L);
+  if (rc) return rc;
+  if (!S || !IO) return set_err(MDG_E_INVALID, "null state/io");
+  if (!S->reset_ts || !IO->pre_price) return set_err(MDG_E_INVALID, "state.reset_ts / io.pre_price is null");
+  if (L->window < 1 || L->head < 0 || L->head >= L->window) return set_err(MDG_E_INVALID, "bad window/head");
+  if (fill_ticks < 1) fill_ticks = 1;
+  if (fill_ticks > L->window) return set_err(MDG_E_INVALID, "fill_ticks > window");
+  const int64_t N = L->n_envs;
+  if (N == 0) return MDG_OK;
+  if (N > 2147483647) return set_err(MDG_E_UNSUPPORTED, "n_envs too large for the reset list");
+  const int nn = P->n_normals > 0 ? P->n_normals : 1;
+  const int64_t list_bytes = 4 * ((N + 63) / 64 * 64);
+  const int64_t per_env = 8 * (int64_t)fill_ticks * nn;
+  const int64_t cap64 = (workspace_bytes - 256 - list_bytes) / per_env;
+  if (cap64 < 1) return set_err(MDG_E_INVALID, "reset workspace too small (see mdg_reset_workspace_bytes)");
+  ResetWsArgs a;
+  a.P = *P; a.S = *S; a.IO = *IO; a.L = *L;
+  a.mask = mask; a.fill_ticks = fill_ticks; a.clear_nstep = clear_nstep;
+  a.count = (int*)workspace;
+  a.list = (int*)((char*)workspace + 256);
+  a.scratch = (double*)((char*)workspace + 256 + list_bytes);
+  a.cap = (int)(cap64 < N ? cap64 : N);
+  a.pass = 0;
+  cudaStream_t st = (cudaStream_t)L->stream;
+  cudaError_t ce = cudaMemsetAsync(a.count, 0, sizeof(int), st);
+  if (ce != cudaSuccess) return cuda_err(ce, "mdg_reset_ws memset");
+  reset_scan_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(a);
+  const int passes = (int)((N + a.cap - 1) / a.cap);
+  const int nb = (P->n_normals + 1) / 2 > 0 ? (P->n_normals + 1) / 2 : 1;
+  for (int p = 0; p < passes; ++p) {
+    a.pass = p;
+    // grids sized for a full pass but capped: the kernels are grid-stride and exit at once past the list end
+    int64_t rng_items = (int64_t)a.cap * fill_ticks * (IO->normals ? nn : nb);
+    unsigned g1 = (unsigned)((rng_items + 255) / 256 < 148 * 32 ? (rng_items + 255) / 256 : 148 * 32);
+    reset_rng_kernel<<<g1 ? g1 : 1, 256, 0, st>>>(a);
+    int64_t rec_items = (int64_t)a.cap * P->n_assets;
+    unsigned g2 = (unsigned)((rec_items + 127) / 128 < 148 * 16 ? (rec_items + 127) / 128 : 148 * 16);
+    reset_recur_kernel<<<g2 ? g2 : 1, 128, 0, st>>>(a);
+  }
+  return cuda_err(cudaGetLastError(), "mdg_reset_ws launch");
 }
 
 extern "C" int mdg_init_state(const MdgParams* P, const MdgReward* R, const MdgState* S, const MdgLaunch* L) {
@@ -292,6 +520,7 @@ extern "C" int mdg_sizeof(int which) {
     case 4: return (int)sizeof(MdgStepIO);
     case 5: return (int)sizeof(MdgLaunch);
     case 6: return (int)sizeof(MdgDerived);
+    case 7: return (int)sizeof(MdgWindow);
   }
   return -1;
 }

@@ -129,10 +129,13 @@ __device__ __forceinline__ double col_sum(const double* col, int n, int sstride,
 }
 
 struct WindowArgs {
-  const double* ring;  // [k][F][N]
+  const double* ring;        // [k][F][N]
+  const double* prefix;      // [N][k][F] rows of the last reset's history fill, or nullptr
+  const int64_t* timestamp;  // [N] (nullptr: every row comes from the ring)
+  const int64_t* reset_ts;   // [N]
   void* out;
   int64_t N;
-  int F, k, head, n_valid, norm, out_dtype, layout;
+  int F, k, head, n_valid, norm, out_dtype, layout, flat_prefix;
   int envs;     // envs per block (blockDim.x)
   int sstride;  // smem stride between rows s (doubles)
   int estride;  // smem stride between envs   (doubles)
@@ -150,11 +153,19 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
   int slot0 = (a.head - (nv - 1)) % k;
   if (slot0 < 0) slot0 += k;
 
-  // phase 1: coalesced ring reads (consecutive envs), column into smem
+  // phase 1: coalesced ring reads (consecutive envs), column into smem.  Rows older than the env's last
+  // reset are not in the ring: they come from the env-major prefix buffer (prices) or are flat (portfolio).
   if (live) {
     int slot = slot0;
+    long long since = 0x7fffffff;  // ring rows written since the last reset (the newest row always is one)
+    if (a.timestamp) since = a.timestamp[e] - a.reset_ts[e] + 1;
     for (int s = 0; s < nv; ++s) {
-      col[s * a.sstride] = a.ring[((int64_t)slot * F + f) * a.N + e];
+      const int age = nv - 1 - s;
+      double v;
+      if (age < since) v = a.ring[((int64_t)slot * F + f) * a.N + e];
+      else if (a.prefix) v = a.prefix[((int64_t)e * k + (k - 1 - (age - (since - 1)))) * F + f];
+      else v = (f == 0) ? 1. : 0.;  // flat portfolio: ledgerNormedFull == [1, 0, ..., 0]
+      col[s * a.sstride] = v;
       if (++slot == k) slot = 0;
     }
   }
@@ -239,14 +250,12 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
   }
 }
 
-__global__ void time_kernel(const int64_t* ring, int64_t N, int k, int head, int nv, int64_t* out) {
+__global__ void time_kernel(const int64_t* timestamp, int64_t N, int nv, int64_t* out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * nv) return;
   const int64_t e = idx / nv;
   const int s = (int)(idx - e * nv);
-  int slot = (head - (nv - 1) + s) % k;
-  if (slot < 0) slot += k;
-  out[idx] = ring[(int64_t)slot * N + e];
+  out[idx] = timestamp[e] - (nv - 1 - s);  // every window row is exactly one generator tick
 }
 
 // ---------------------------------------------------------------------------
@@ -362,20 +371,22 @@ extern "C" int mdg_derived(const MdgParams* P, const MdgState* S, const MdgDeriv
   return cuda_err(cudaGetLastError(), "mdg_derived launch");
 }
 
-extern "C" int mdg_materialise_window(const double* ring, int64_t n_envs, int32_t n_feats, int32_t window,
-                                      int32_t head, int32_t n_valid, int32_t norm_type, void* out,
-                                      int32_t out_dtype, int32_t out_layout, void* stream) {
-  if (!ring || !out) return set_err(MDG_E_INVALID, "null ring/out");
+extern "C" int mdg_materialise_window(const MdgWindow* w) {
+  if (!w || !w->ring || !w->out) return set_err(MDG_E_INVALID, "null window/ring/out");
+  const int n_feats = w->n_feats, window = w->window, head = w->head, n_valid = w->n_valid;
   if (n_feats < 1 || n_feats > 64) return set_err(MDG_E_UNSUPPORTED, "n_feats must be in 1..64");
   if (window < 1 || head < 0 || head >= window || n_valid < 1 || n_valid > window)
     return set_err(MDG_E_INVALID, "bad window/head/n_valid");
-  if (norm_type < MDG_NORM_NONE || norm_type > MDG_NORM_EXPANDING) return set_err(MDG_E_INVALID, "bad norm_type");
-  if (out_dtype != MDG_DTYPE_F64 && out_dtype != MDG_DTYPE_F32) return set_err(MDG_E_INVALID, "bad out_dtype");
-  if (out_layout != MDG_LAYOUT_NKF && out_layout != MDG_LAYOUT_NFK) return set_err(MDG_E_INVALID, "bad layout");
-  if (n_envs <= 0) return n_envs == 0 ? MDG_OK : set_err(MDG_E_INVALID, "n_envs < 0");
+  if (w->norm_type < MDG_NORM_NONE || w->norm_type > MDG_NORM_EXPANDING) return set_err(MDG_E_INVALID, "bad norm_type");
+  if (w->out_dtype != MDG_DTYPE_F64 && w->out_dtype != MDG_DTYPE_F32) return set_err(MDG_E_INVALID, "bad out_dtype");
+  if (w->out_layout != MDG_LAYOUT_NKF && w->out_layout != MDG_LAYOUT_NFK) return set_err(MDG_E_INVALID, "bad layout");
+  if (w->timestamp && !w->reset_ts) return set_err(MDG_E_INVALID, "timestamp given without reset_ts");
+  if (w->timestamp && !w->prefix && !w->flat_prefix) return set_err(MDG_E_INVALID, "no prefix source for rows older than the reset");
+  if (w->n_envs <= 0) return w->n_envs == 0 ? MDG_OK : set_err(MDG_E_INVALID, "n_envs < 0");
   WindowArgs a;
-  a.ring = ring; a.out = out; a.N = n_envs; a.F = n_feats; a.k = window; a.head = head; a.n_valid = n_valid;
-  a.norm = norm_type; a.out_dtype = out_dtype; a.layout = out_layout;
+  a.ring = w->ring; a.prefix = w->prefix; a.timestamp = w->timestamp; a.reset_ts = w->reset_ts;
+  a.out = w->out; a.N = w->n_envs; a.F = n_feats; a.k = window; a.head = head; a.n_valid = n_valid;
+  a.norm = w->norm_type; a.out_dtype = w->out_dtype; a.layout = w->out_layout; a.flat_prefix = w->flat_prefix;
   // envs per block: power of two, 8..32, about 128-256 threads, tile <= ~96 KB
   int envs = 32;
   while (envs > 8 && envs * n_feats > 256) envs >>= 1;
@@ -392,20 +403,18 @@ extern "C" int mdg_materialise_window(const double* ring, int64_t n_envs, int32_
   if (smem > 200 * 1024) return set_err(MDG_E_UNSUPPORTED, "window tile does not fit shared memory");
   cudaError_t ce = cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return cuda_err(ce, "window smem attr");
-  const unsigned grid = (unsigned)((n_envs + envs - 1) / envs);
-  window_kernel<<<grid, dim3(envs, n_feats), smem, (cudaStream_t)stream>>>(a);
+  const unsigned grid = (unsigned)((w->n_envs + envs - 1) / envs);
+  window_kernel<<<grid, dim3(envs, n_feats), smem, (cudaStream_t)w->stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_materialise_window launch");
 }
 
-extern "C" int mdg_materialise_time(const int64_t* ring, int64_t n_envs, int32_t window, int32_t head,
-                                    int32_t n_valid, int64_t* out, void* stream) {
-  if (!ring || !out) return set_err(MDG_E_INVALID, "null ring/out");
-  if (window < 1 || head < 0 || head >= window || n_valid < 1 || n_valid > window)
-    return set_err(MDG_E_INVALID, "bad window/head/n_valid");
+extern "C" int mdg_materialise_time(const int64_t* timestamp, int64_t n_envs, int32_t n_valid, int64_t* out,
+                                    void* stream) {
+  if (!timestamp || !out) return set_err(MDG_E_INVALID, "null timestamp/out");
+  if (n_valid < 1) return set_err(MDG_E_INVALID, "bad n_valid");
   if (n_envs <= 0) return n_envs == 0 ? MDG_OK : set_err(MDG_E_INVALID, "n_envs < 0");
   const int64_t total = n_envs * n_valid;
-  time_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ring, n_envs, window, head,
-                                                                                 n_valid, out);
+  time_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(timestamp, n_envs, n_valid, out);
   return cuda_err(cudaGetLastError(), "mdg_materialise_time launch");
 }
 

@@ -57,7 +57,7 @@ struct GenCtx {
   const double* z;         // this env's normals for this tick: z[slot * zstride] (shared memory column)
   int zstride;
   const double* uniforms;  // [n_uniforms][N] for this tick (validation mode) or nullptr
-  int64_t N, e;
+  int64_t N, e, gstride;
   uint32_t gid, k0, k1, t_lo, t_hi;
 };
 
@@ -67,6 +67,7 @@ __device__ __forceinline__ void ctx_init(GenCtx& c, const double* z, int zstride
   c.zstride = zstride;
   c.uniforms = uniforms;
   c.N = L.n_envs;
+  c.gstride = L.n_envs;
   c.e = e;
   c.gid = (uint32_t)(L.env_offset + e);
   c.k0 = (uint32_t)L.seed;
@@ -113,7 +114,7 @@ static __device__ __noinline__ double draw_uniform(const GenCtx& c, int slot) {
 struct LazyDraws {
   const double* normals;   // [n_normals][N] for this tick (validation mode) or nullptr
   const double* uniforms;  // [n_uniforms][N] for this tick (validation mode) or nullptr
-  int64_t N, e;
+  int64_t N, e, gstride;
   uint32_t gid, k0, k1, t_lo, t_hi;
   int cached_block;
   double z0, z1;
@@ -147,7 +148,7 @@ static __device__ __noinline__ double draw_uniform(LazyDraws& c, int slot) {
 struct TickDraws {
   const double* z;         // z[slot]
   const double* uniforms;  // [n_uniforms][N] for this tick (validation mode) or nullptr
-  int64_t N, e;
+  int64_t N, e, gstride;
   uint32_t gid, k0, k1, t_lo, t_hi;
 };
 __device__ __forceinline__ double draw_normal(TickDraws& c, int slot) { return c.z[slot]; }
@@ -185,7 +186,7 @@ template <class D>
 static __device__ __noinline__ double gen_tick(const MdgAssetGen& g, double price, double* __restrict__ gs,
                                                D& d, double& pair_mean) {
   const double* p = g.p;
-  const int64_t N = d.N;
+  const int64_t N = d.gstride;  // distance between this asset's generator-state rows
   switch (g.type) {
     case MDG_GEN_SYNTH: {  // DataSource.cpp:535-543
       const double x = gs[0];

@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __gr
   } else {
     // ---- generic path (Composite / sine / trend sources): one asset per iteration
     LazyDraws dr;
-    dr.N = N; dr.e = e;
+    dr.N = N; dr.e = e; dr.gstride = N;
     dr.gid = gid; dr.k0 = k0; dr.k1 = k1; dr.t_lo = t_lo; dr.t_hi = t_hi;
     dr.cached_block = -1;
     dr.normals = a.IO.normals; dr.uniforms = a.IO.uniforms;
@@ -567,7 +567,6 @@ __global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __gr
       cosv_pp = w0 * w0; cosv_qq = d0 * d0; cosv_pq = w0 * d0;
     }
   }
-  a.IO.obs_time[(int64_t)head * N + e] = ts + 1;
   const int ra = a.R.reduce_rewards ? 1 : na;
   const double inv_prev = 1. / prevEq;
   const int len_before = (shaping && a.R.nstep > 1) ? S.nstep_len[e] : 0;

@@ -60,6 +60,20 @@ class _View:
         return self._env.checkRisk(*a)
 
 
+# reset workspaces are scratch (no state between calls): one per (device, stream), shared by all Envs
+_RESET_WS = {}
+
+
+def _reset_workspace(lib_, P, n_envs, fill_ticks, device):
+    need = int(lib_.mdg_reset_workspace_bytes(C.byref(P), n_envs, fill_ticks))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _RESET_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _RESET_WS[key] = ws
+    return ws
+
+
 class Env:
     def __init__(self, dataSourceType, initCash=1_000_000., config=None, *, n_envs=None, device=None,
                  window=None, seed=None, env_offset=0, reward=None):
@@ -120,10 +134,11 @@ class Env:
             price=z((nA, N), **f8), ledger=z((nA, N), **f8), mean_entry=z((nA, N), **f8),
             borrowed=z((nA, N), **f8), cash=z((N,), **f8), gstate=z((max(1, self.P.n_gstate), N), **f8),
             timestamp=z((N,), dtype=torch.int64, device=dev), folds=z((5, N), **f8),
+            reset_ts=z((N,), dtype=torch.int64, device=dev),
             shaper_A=z((self.ra, N), **f8), shaper_B=z((self.ra, N), **f8),
             nstep_ring=z((self.R.nstep, self.ra, N), **f8), nstep_len=z((N,), dtype=torch.int32, device=dev),
             obs_price=z((k, nA, N), **f8), obs_port=z((k, nA + 1, N), **f8),
-            obs_time=z((k, N), dtype=torch.int64, device=dev),
+            pre_price=z((N, k, nA), **f8),
             reward=z((N,), **f8), done=z((N,), dtype=torch.bool, device=dev),
             trans_price=z((nA, N), **f8), trans_units=z((nA, N), **f8), trans_cost=z((nA, N), **f8),
             risk=z((nA, N), dtype=torch.uint8, device=dev), margin_call=z((N,), dtype=torch.bool, device=dev),
@@ -133,11 +148,11 @@ class Env:
         )
         S = A.MdgState()
         for name in ("price", "ledger", "mean_entry", "borrowed", "cash", "gstate", "timestamp", "shaper_A",
-                     "shaper_B", "nstep_ring", "nstep_len", "folds"):
+                     "shaper_B", "nstep_ring", "nstep_len", "reset_ts", "folds"):
             setattr(S, name, self.t[name].data_ptr())
         self._S = S
         IO = A.MdgStepIO()
-        for name in ("obs_price", "obs_port", "obs_time", "reward", "done", "trans_price", "trans_units",
+        for name in ("obs_price", "obs_port", "pre_price", "reward", "done", "trans_price", "trans_units",
                      "trans_cost", "risk", "margin_call", "agent_reward", "shaped_reward", "n_popped"):
             setattr(IO, name, self.t[name].data_ptr())
         self._IO = IO
@@ -189,15 +204,18 @@ class Env:
             m = m.to(device=self.device, dtype=torch.uint8).contiguous()
             if tuple(m.shape) != (self.N,):
                 raise ValueError(f"mask must have shape ({self.N},)")
-        check(self._lib.mdg_reset(C.byref(self.P), C.byref(self._S), C.byref(io), C.byref(self._launch()),
-                                  None if m is None else m.data_ptr(), int(fill_ticks), int(clear_nstep)))
-        self.launches += 1
+        ws = _reset_workspace(self._lib, self.P, self.N, int(fill_ticks), self.device)
+        check(self._lib.mdg_reset_ws(C.byref(self.P), C.byref(self._S), C.byref(io), C.byref(self._launch()),
+                                     None if m is None else m.data_ptr(), int(fill_ticks), int(clear_nstep),
+                                     ws.data_ptr(), ws.numel()))
+        # scan + (rng, recur) per pass of at most 32,768 listed envs
+        self.launches += 1 + 2 * max(1, -(-self.N // 32768))
         self._version += 1
         del keep
 
     def _state(self):
         t = self.t
-        return State(t["obs_price"][self.head].t(), t["obs_port"][self.head].t(), t["obs_time"][self.head],
+        return State(t["obs_price"][self.head].t(), t["obs_port"][self.head].t(), t["timestamp"],
                      _ring=(self, self._version))
 
     def reset(self, mask=None, fill_history=False, normals=None, uniforms=None):
@@ -259,7 +277,7 @@ class Env:
             if auto_reset:
                 self._reset_launch(self.t["done"], self.k, True, None, None)
         t = self.t
-        resp = BrokerResponse("", t["obs_time"][self.head], t["trans_price"].t(), t["trans_units"].t(),
+        resp = BrokerResponse("", t["timestamp"], t["trans_price"].t(), t["trans_units"].t(),
                               t["trans_cost"].t(), t["risk"].t(), t["margin_call"])
         return self._state(), t["reward"], t["done"], EnvInfo(resp, False)
 
@@ -414,31 +432,34 @@ class Env:
         if out is None:
             out = torch.empty(shape, dtype=dtype, device=self.device)
         dt = A.DTYPE_F32 if out.dtype == torch.float32 else A.DTYPE_F64
-        with torch.cuda.device(self.device):
-            check(self._lib.mdg_materialise_window(self.t["obs_price"].data_ptr(), self.N, self.nA, self.k, self.head,
-                                                   nv, norm, out.data_ptr(), dt,
-                                                   A.LAYOUT_NFK if channels_first else A.LAYOUT_NKF,
-                                                   torch.cuda.current_stream(self.device).cuda_stream))
-        self.launches += 1
+        self._window_launch(self.t["obs_price"], self.t["pre_price"], 0, self.nA, nv, norm, out, dt,
+                            A.LAYOUT_NFK if channels_first else A.LAYOUT_NKF)
         return out
 
+    def _window_launch(self, ring, prefix, flat_prefix, n_feats, nv, norm, out, dt, layout):
+        w = A.MdgWindow(ring=ring.data_ptr(), prefix=None if prefix is None else prefix.data_ptr(),
+                        timestamp=self.t["timestamp"].data_ptr(), reset_ts=self.t["reset_ts"].data_ptr(),
+                        n_envs=self.N, n_feats=n_feats, window=self.k, head=self.head, n_valid=nv, norm_type=norm,
+                        flat_prefix=flat_prefix, out_dtype=dt, out_layout=layout, out=out.data_ptr(),
+                        stream=torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            check(self._lib.mdg_materialise_window(C.byref(w)))
+        self.launches += 1
+
     def portfolio_window(self, n_valid=None):
-        """(N, n_valid, nA+1) window of ledgerNormedFull rows, oldest first."""
+        """(N, n_valid, nA+1) window of ledgerNormedFull rows, oldest first (rows older than the env's last
+        reset are the flat portfolio [1,0,...,0] of its history fill)."""
         nv = self.n_valid if n_valid is None else int(n_valid)
         out = torch.empty((self.N, nv, self.nA + 1), dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
-            check(self._lib.mdg_materialise_window(self.t["obs_port"].data_ptr(), self.N, self.nA + 1, self.k,
-                                                   self.head, nv, A.NORM_NONE, out.data_ptr(), A.DTYPE_F64,
-                                                   A.LAYOUT_NKF, torch.cuda.current_stream(self.device).cuda_stream))
-        self.launches += 1
+        self._window_launch(self.t["obs_port"], None, 1, self.nA + 1, nv, A.NORM_NONE, out, A.DTYPE_F64, A.LAYOUT_NKF)
         return out
 
     def time_window(self, n_valid=None):
         nv = self.n_valid if n_valid is None else int(n_valid)
         out = torch.empty((self.N, nv), dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
-            check(self._lib.mdg_materialise_time(self.t["obs_time"].data_ptr(), self.N, self.k, self.head, nv,
-                                                 out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+            check(self._lib.mdg_materialise_time(self.t["timestamp"].data_ptr(), self.N, nv, out.data_ptr(),
+                                                 torch.cuda.current_stream(self.device).cuda_stream))
         self.launches += 1
         return out
 

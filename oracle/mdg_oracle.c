@@ -736,6 +736,7 @@ void orc_batch_export_state(const OrcBatch *b, const MdgState *s) {
       if (s->shaper_B) s->shaper_B[c * N + i] = e->B[c];
     }
     if (s->nstep_len) s->nstep_len[i] = e->ring_len;
+    /* s->reset_ts / s->folds are caches of the CUDA path; the oracle has no counterpart */
   }
 }
 
@@ -743,7 +744,6 @@ static void write_row(const MdgStepIO *io, const MdgLaunch *L, int nA, int64_t N
                       int slot, const OrcStepOut *o) {
   for (int j = 0; j < nA; ++j) io->obs_price[((int64_t)slot * nA + j) * N + i] = o->price[j];
   for (int j = 0; j < nA + 1; ++j) io->obs_port[((int64_t)slot * (nA + 1) + j) * N + i] = o->port[j];
-  io->obs_time[(int64_t)slot * N + i] = o->timestamp;
   (void)L;
 }
 

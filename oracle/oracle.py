@@ -249,7 +249,6 @@ class OracleBatch:
         f8 = np.float64
         self.obs_price = np.zeros((k, nA, N), f8)
         self.obs_port = np.zeros((k, nA + 1, N), f8)
-        self.obs_time = np.zeros((k, N), np.int64)
         self.reward = np.zeros(N, f8)
         self.done = np.zeros(N, np.uint8)
         self.trans_price = np.zeros((nA, N), f8)
@@ -274,7 +273,7 @@ class OracleBatch:
         self._keep = [np.ascontiguousarray(x, dtype=np.float64) if x is not None else None
                       for x in (units, normals, uniforms)]
         io.units, io.normals, io.uniforms = (_ptr(x) for x in self._keep)
-        for name in ("obs_price", "obs_port", "obs_time", "reward", "done", "trans_price", "trans_units",
+        for name in ("obs_price", "obs_port", "reward", "done", "trans_price", "trans_units",
                      "trans_cost", "risk", "margin_call", "agent_reward", "shaped_reward", "n_popped"):
             setattr(io, name, _ptr(getattr(self, name)))
         return io
@@ -338,6 +337,17 @@ class OracleBatch:
             setattr(dd, k_, _ptr(v))
         self.L.orc_batch_derived(self.h, C.byref(dd))
         return d
+
+    def time_window(self, n_valid=None):
+        """(N, n_valid) timestamps of the window rows (every row is exactly one generator tick)."""
+        nv = self.n_valid if n_valid is None else n_valid
+        ts = self.state()["timestamp"]
+        return ts[:, None] - np.arange(nv - 1, -1, -1)[None, :]
+
+    def port_window(self, n_valid=None):
+        nv = self.n_valid if n_valid is None else n_valid
+        idx = [(self.head - (nv - 1 - s)) % self.k for s in range(nv)]
+        return np.ascontiguousarray(self.obs_port[idx].transpose(2, 0, 1))
 
     def window(self, n_valid=None):
         """price window (N, n_valid, nA) oldest first, as StackerDiscrete.current_data (un-normalised)."""

@@ -119,6 +119,19 @@ def cpu(x):
     return x.detach().cpu().numpy()
 
 
+def compare_windows(env, orc, exact):
+    """The (N,k,*) windows an agent would get: ring rows written by steps + the env-major rows of the last
+    reset's history fill (prices) / the flat portfolio (weights), against the oracle's rings."""
+    nv = orc.n_valid
+    w = cpu(env.window(None, n_valid=nv))
+    if exact:
+        assert same_bits(w, orc.window(nv)), "price window"
+    else:
+        close(w, orc.window(nv))
+    close(cpu(env.portfolio_window(nv)), orc.port_window(nv), rtol=1e-13 if exact else RTOL, atol=1e-15 if exact else 1e-10)
+    assert np.array_equal(cpu(env.time_window(nv)), orc.time_window(nv)), "time window"
+
+
 def compare_step(env, orc, exact_prices, t, shaped=False):
     T = env.t
     tag = f"step {t}"
@@ -145,7 +158,6 @@ def compare_step(env, orc, exact_prices, t, shaped=False):
         close(cpu(T["trans_cost"]), orc.trans_cost)
         close(cpu(T["obs_price"][env.head]), orc.obs_price[orc.head])
         close(cpu(T["obs_port"][env.head]), orc.obs_port[orc.head], atol=1e-10)
-    assert np.array_equal(cpu(T["obs_time"][env.head]), orc.obs_time[orc.head]), tag + " obs time row"
     close(cpu(T["reward"]), orc.reward)
     if shaped:
         close(cpu(T["agent_reward"]), orc.agent_reward)
@@ -173,12 +185,7 @@ def run_case(case, N, T, window=8, reward=None, margins=(1., .25), costs=(0., 0.
     nz, uz = noise(rng, P, N, ticks=window)
     env.reset(fill_history=True, normals=nz, uniforms=uz)
     orc.reset(fill_ticks=window, normals=nz, uniforms=uz)
-    if exact:
-        assert same_bits(cpu(env.t["obs_price"]), orc.obs_price)
-        assert same_bits(cpu(env.t["obs_port"]), orc.obs_port)  # flat portfolio rows: exactly [1, 0, ...]
-    else:
-        close(cpu(env.t["obs_price"]), orc.obs_price)
-    assert np.array_equal(cpu(env.t["obs_time"]), orc.obs_time)
+    compare_windows(env, orc, exact)
     n_done = 0
     for t in range(T):
         units = gen_units(rng, orc, N, nA, scale)
@@ -193,9 +200,7 @@ def run_case(case, N, T, window=8, reward=None, margins=(1., .25), costs=(0., 0.
             env.reset(mask=torch.from_numpy(orc.done.copy()), fill_history=True, normals=nz, uniforms=uz)
             orc.reset(mask=orc.done.copy(), fill_ticks=window, normals=nz, uniforms=uz)
             assert np.array_equal(cpu(env.t["ledger"]), orc.state()["ledger"])
-            assert np.array_equal(cpu(env.t["obs_time"]), orc.obs_time)
-            if exact:
-                assert same_bits(cpu(env.t["obs_price"]), orc.obs_price)
+            compare_windows(env, orc, exact)
     # derived accounting at the end
     d_o = orc.derived()
     d_g = env._derived()

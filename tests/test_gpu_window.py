@@ -29,6 +29,8 @@ def load_ring(env, rows, newest_index):
         env.t["obs_price"][r % k].copy_(torch.from_numpy(np.ascontiguousarray(rows[r])))
     env.head = newest_index % k
     env.n_valid = min(k, R)
+    # pretend the rows were written by steps: no row is older than the env's last reset
+    env.t["reset_ts"].fill_(-(10 ** 9))
 
 
 @pytest.mark.parametrize("norm", NORMS)
