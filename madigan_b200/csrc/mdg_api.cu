@@ -215,23 +215,34 @@ __global__ void __launch_bounds__(256) reset_rng_kernel(const __grid_constant__ 
   }
   const int nb = (nn + 1) >> 1;
   const uint32_t k0 = (uint32_t)a.L.seed, k1 = (uint32_t)(a.L.seed >> 32);
-  const int64_t total = (int64_t)here * fill * nb;
-  for (int64_t item = (int64_t)blockIdx.x * 256 + threadIdx.x; item < total; item += (int64_t)gridDim.x * 256) {
-    const int b = (int)(item % nb);
-    const int64_t r = item / nb;
-    const int t = (int)(r % fill), d = (int)(r / fill);
+  // one block walks whole envs (grid-stride); inside an env, thread j = tick * nb + block.  All index
+  // arithmetic is 32-bit with a multiply-high reciprocal (64-bit div/mod cost more than the Box-Muller).
+  const uint32_t per_env = (uint32_t)(fill * nb);
+  const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)nb - 1) / (uint32_t)nb);  // ceil(2^32 / nb)
+  for (int d = blockIdx.x; d < here; d += gridDim.x) {
     const int64_t e = a.list[first + d];
-    const unsigned long long tick = (unsigned long long)(a.S.timestamp[e] - fill + t);
-    uint64_t x0, x1;
-    philox4x32_10((uint32_t)(a.L.env_offset + e), (uint32_t)b, (uint32_t)tick, (uint32_t)(tick >> 32), k0, k1, x0, x1);
-    const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
-    const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
-    const double r2 = sqrt(-2.0 * fast_log_pos(u1));
-    double sn, cs;
-    fast_sincos_2pi(u2, sn, cs);
-    double* z = a.scratch + ((int64_t)d * fill + t) * nn;
-    z[2 * b] = r2 * cs;
-    if (2 * b + 1 < nn) z[2 * b + 1] = r2 * sn;
+    const uint32_t gid = (uint32_t)(a.L.env_offset + e);
+    const unsigned long long tick0 = (unsigned long long)(a.S.timestamp[e] - fill);
+    double* zenv = a.scratch + (int64_t)d * fill * nn;
+    for (uint32_t j = threadIdx.x; j < per_env; j += 256) {
+      const uint32_t t = (nb == 1) ? j : __umulhi(j, magic);  // j / nb, exact for j < 2^16 (magic overflows for nb == 1)
+      const uint32_t b = j - t * (uint32_t)nb;
+      const unsigned long long tick = tick0 + t;
+      uint64_t x0, x1;
+      philox4x32_10(gid, b, (uint32_t)tick, (uint32_t)(tick >> 32), k0, k1, x0, x1);
+      const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
+      const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
+      const double r2 = sqrt(-2.0 * fast_log_pos(u1));
+      double sn, cs;
+      fast_sincos_2pi(u2, sn, cs);
+      double* z = zenv + t * (uint32_t)nn + 2 * b;
+      if ((nn & 1) == 0) {
+        *reinterpret_cast<double2*>(z) = make_double2(r2 * cs, r2 * sn);  // rows of an even length stay 16-byte aligned
+      } else {
+        z[0] = r2 * cs;
+        if (2 * (int)b + 1 < nn) z[1] = r2 * sn;
+      }
+    }
   }
 }
 
@@ -257,10 +268,12 @@ __global__ void __launch_bounds__(128) reset_recur_kernel(const __grid_constant_
   const double cash = P.init_cash;
   const double eq = cash + 0. - 0.;
   const bool eq_plain = eq > 0. && eq < 1e300;  // then (0*p)/eq == 0*p exactly
-  const int64_t total = (int64_t)here * nlead;
+  const uint32_t total = (uint32_t)here * (uint32_t)nlead;  // < 2^31 * 16 would overflow: here <= cap <= 65536
+  const uint32_t lmagic = (uint32_t)((0x100000000ull + (uint32_t)nlead - 1) / (uint32_t)nlead);
   // item = d * nlead + l: the groups of one env are neighbouring lanes -> they read one contiguous scratch row
-  for (int64_t item = (int64_t)blockIdx.x * 128 + threadIdx.x; item < total; item += (int64_t)gridDim.x * 128) {
-    const int d = (int)(item / nlead), l = (int)(item - (int64_t)d * nlead);
+  for (uint32_t item = blockIdx.x * 128 + threadIdx.x; item < total; item += gridDim.x * 128) {
+    const int d = (nlead == 1) ? (int)item : (int)__umulhi(item, lmagic);  // item / nlead
+    const int l = (int)(item - (uint32_t)d * (uint32_t)nlead);
     const int64_t e = a.list[first + d];
     const int i0 = s_leader[l];
     const int cnt = (P.gen[i0].type == MDG_GEN_OUPAIR) ? 2 : 1;
@@ -272,26 +285,51 @@ __global__ void __launch_bounds__(128) reset_recur_kernel(const __grid_constant_
                        : P.gen[i0].type == MDG_GEN_SIMPLETREND ? 2 : 1);
     for (int r = 0; r < ngs; ++r) gsl[r] = a.S.gstate[(int64_t)(gslot0 + r) * N + e];
     for (int c = 0; c < cnt; ++c) pr[c] = a.S.price[(int64_t)(i0 + c) * N + e];
-    TickDraws dr;
-    dr.N = N; dr.e = e; dr.gstride = 1;
-    dr.gid = (uint32_t)(a.L.env_offset + e);
-    dr.k0 = (uint32_t)a.L.seed; dr.k1 = (uint32_t)(a.L.seed >> 32);
     const long long ts0 = a.S.timestamp[e] - fill;
     const double* zrow = a.scratch + (int64_t)d * fill * nn;
+    double* prow = a.IO.pre_price + ((int64_t)e * k + (k - fill)) * na + i0;
+    if (P.gen[i0].type == MDG_GEN_OUPAIR) {
+      // OUPair::getData (DataSource.cpp:1232-1240) inlined; the next tick's three normals are loaded while
+      // the current tick is computed (the recurrence itself is ~10 dependent flops per tick)
+      const MdgAssetGen& g0 = P.gen[i0];
+      const MdgAssetGen& g1 = P.gen[i0 + 1];
+      const double theta0 = g0.p[0], phi0 = g0.p[1], noise = g0.p[2], theta1 = g1.p[0], phi1 = g1.p[1];
+      const int s_rw = g0.nslot_aux, s_0 = g0.nslot, s_1 = g1.nslot;
+      double m = gsl[0];
+      double z_rw = zrow[s_rw], z0 = zrow[s_0], z1 = zrow[s_1];
+#pragma unroll 2
+      for (int t = 0; t < fill; ++t) {
+        const double c_rw = z_rw, c0 = z0, c1 = z1;
+        if (t + 1 < fill) {
+          const double* zn = zrow + (int64_t)(t + 1) * nn;
+          z_rw = zn[s_rw]; z0 = zn[s_0]; z1 = zn[s_1];
+        }
+        m += m * (c_rw * noise);
+        pr[0] += (theta0 * (m - pr[0])) + m * (c0 * phi0);
+        pr[1] += (theta1 * (m - pr[1])) + m * (c1 * phi1);
+        if ((na & 1) == 0) {  // 16-byte aligned: one vector store, the env's pairs fill whole sectors together
+          *reinterpret_cast<double2*>(prow + (int64_t)t * na) = make_double2(pr[0], pr[1]);
+        } else {
+          prow[(int64_t)t * na] = pr[0];
+          prow[(int64_t)t * na + 1] = pr[1];
+        }
+      }
+      gsl[0] = m;
+    } else {
+      TickDraws dr;
+      dr.N = N; dr.e = e; dr.gstride = 1;
+      dr.gid = (uint32_t)(a.L.env_offset + e);
+      dr.k0 = (uint32_t)a.L.seed; dr.k1 = (uint32_t)(a.L.seed >> 32);
 #pragma unroll 1
-    for (int t = 0; t < fill; ++t) {
-      const long long tick = ts0 + t;
-      dr.t_lo = (uint32_t)(unsigned long long)tick;
-      dr.t_hi = (uint32_t)((unsigned long long)tick >> 32);
-      dr.z = zrow + (int64_t)t * nn;
-      dr.uniforms = a.IO.uniforms ? a.IO.uniforms + (int64_t)t * P.n_uniforms * N : nullptr;
-      double pair_mean = 0.;
-#pragma unroll 1
-      for (int c = 0; c < cnt; ++c) {
-        const MdgAssetGen& g = P.gen[i0 + c];
-        pr[c] = gen_tick(g, pr[c], gsl, dr, pair_mean);  // role 1 of a pair has no rows of its own (pair_mean)
-        // env-major history row: the groups of one env (neighbouring lanes) fill one contiguous nA*8-byte run
-        a.IO.pre_price[((int64_t)e * k + (k - fill + t)) * na + i0 + c] = pr[c];
+      for (int t = 0; t < fill; ++t) {
+        const long long tick = ts0 + t;
+        dr.t_lo = (uint32_t)(unsigned long long)tick;
+        dr.t_hi = (uint32_t)((unsigned long long)tick >> 32);
+        dr.z = zrow + (int64_t)t * nn;
+        dr.uniforms = a.IO.uniforms ? a.IO.uniforms + (int64_t)t * P.n_uniforms * N : nullptr;
+        double pair_mean = 0.;
+        pr[0] = gen_tick(P.gen[i0], pr[0], gsl, dr, pair_mean);
+        prow[(int64_t)t * na] = pr[0];
       }
     }
     for (int c = 0; c < cnt; ++c) {  // newest row = current state, also in the ring
@@ -432,8 +470,8 @@ extern "C" int mdg_reset(const MdgParams* P, const MdgState* S, const MdgStepIO*
 extern "C" int64_t mdg_reset_workspace_bytes(const MdgParams* P, int64_t n_envs, int fill_ticks) {
   if (!P || n_envs < 0) return -1;
   if (fill_ticks < 1) fill_ticks = 1;
-  // header (count) + list + scratch for min(N, 32768) listed envs per pass
-  const int64_t cap = n_envs < 32768 ? n_envs : 32768;
+  // header (count) + list + scratch for min(N, 65536) listed envs per pass
+  const int64_t cap = n_envs < 65536 ? n_envs : 65536;
   return 256 + 4 * ((n_envs + 63) / 64 * 64) + 8 * cap * (int64_t)fill_ticks * (P->n_normals > 0 ? P->n_normals : 1);
 }
 
@@ -473,8 +511,8 @@ extern "C" int mdg_reset_ws(const MdgParams* P, const MdgState* S, const MdgStep
   for (int p = 0; p < passes; ++p) {
     a.pass = p;
     // grids sized for a full pass but capped: the kernels are grid-stride and exit at once past the list end
-    int64_t rng_items = (int64_t)a.cap * fill_ticks * (IO->normals ? nn : nb);
-    unsigned g1 = (unsigned)((rng_items + 255) / 256 < 148 * 32 ? (rng_items + 255) / 256 : 148 * 32);
+    unsigned g1 = (unsigned)(a.cap < 148 * 8 ? a.cap : 148 * 8);  // one block per listed env, grid-stride
+    (void)nb;
     reset_rng_kernel<<<g1 ? g1 : 1, 256, 0, st>>>(a);
     int64_t rec_items = (int64_t)a.cap * P->n_assets;
     unsigned g2 = (unsigned)((rec_items + 127) / 128 < 148 * 16 ? (rec_items + 127) / 128 : 148 * 16);

@@ -208,8 +208,8 @@ class Env:
         check(self._lib.mdg_reset_ws(C.byref(self.P), C.byref(self._S), C.byref(io), C.byref(self._launch()),
                                      None if m is None else m.data_ptr(), int(fill_ticks), int(clear_nstep),
                                      ws.data_ptr(), ws.numel()))
-        # scan + (rng, recur) per pass of at most 32,768 listed envs
-        self.launches += 1 + 2 * max(1, -(-self.N // 32768))
+        # scan + (rng, recur) per pass of at most 65,536 listed envs
+        self.launches += 1 + 2 * max(1, -(-self.N // 65536))
         self._version += 1
         del keep
 
