@@ -296,22 +296,32 @@ __global__ void __launch_bounds__(128) reset_recur_kernel(const __grid_constant_
       const double theta0 = g0.p[0], phi0 = g0.p[1], noise = g0.p[2], theta1 = g1.p[0], phi1 = g1.p[1];
       const int s_rw = g0.nslot_aux, s_0 = g0.nslot, s_1 = g1.nslot;
       double m = gsl[0];
-      double z_rw = zrow[s_rw], z0 = zrow[s_0], z1 = zrow[s_1];
-#pragma unroll 2
-      for (int t = 0; t < fill; ++t) {
-        const double c_rw = z_rw, c0 = z0, c1 = z1;
-        if (t + 1 < fill) {
-          const double* zn = zrow + (int64_t)(t + 1) * nn;
-          z_rw = zn[s_rw]; z0 = zn[s_0]; z1 = zn[s_1];
+      // chunks of 8 ticks: 24 independent L2 loads in flight, then 8 short dependent updates
+      constexpr int TC = 8;
+#pragma unroll 1
+      for (int t0 = 0; t0 < fill; t0 += TC) {
+        double zr[TC], za[TC], zb[TC];
+#pragma unroll
+        for (int u = 0; u < TC; ++u) {
+          if (t0 + u < fill) {
+            const double* zn = zrow + (int64_t)(t0 + u) * nn;
+            zr[u] = zn[s_rw]; za[u] = zn[s_0]; zb[u] = zn[s_1];
+          }
         }
-        m += m * (c_rw * noise);
-        pr[0] += (theta0 * (m - pr[0])) + m * (c0 * phi0);
-        pr[1] += (theta1 * (m - pr[1])) + m * (c1 * phi1);
-        if ((na & 1) == 0) {  // 16-byte aligned: one vector store, the env's pairs fill whole sectors together
-          *reinterpret_cast<double2*>(prow + (int64_t)t * na) = make_double2(pr[0], pr[1]);
-        } else {
-          prow[(int64_t)t * na] = pr[0];
-          prow[(int64_t)t * na + 1] = pr[1];
+#pragma unroll
+        for (int u = 0; u < TC; ++u) {
+          if (t0 + u < fill) {
+            m += m * (zr[u] * noise);
+            pr[0] += (theta0 * (m - pr[0])) + m * (za[u] * phi0);
+            pr[1] += (theta1 * (m - pr[1])) + m * (zb[u] * phi1);
+            double* dst = prow + (int64_t)(t0 + u) * na;
+            if ((na & 1) == 0) {  // 16-byte aligned: one vector store, the env's pairs fill whole sectors together
+              *reinterpret_cast<double2*>(dst) = make_double2(pr[0], pr[1]);
+            } else {
+              dst[0] = pr[0];
+              dst[1] = pr[1];
+            }
+          }
         }
       }
       gsl[0] = m;
