@@ -1,5 +1,7 @@
 // extern "C" entry points of the step path + the (rare, non-unrolled) reset / init kernels.
-#include "mdg_step_kernel.cuh"
+#include <stdlib.h>
+
+#include "mdg_step_pairs.cuh"
 
 namespace mdg {
 
@@ -456,6 +458,10 @@ extern "C" int mdg_step(const MdgParams* P, const MdgReward* R, const MdgState* 
   }
   const int na = P->n_assets;
   (void)na;
+  // MDG_STEP_KERNEL=ws selects the warp-specialised experiment (mdg_step_pairs.cuh) for all-OU-pairs
+  // configurations; measured slower than the streaming kernel (profiles/r1_notes.md), so it is opt-in.
+  static const bool use_ws = [] { const char* v = getenv("MDG_STEP_KERNEL"); return v && v[0] == 'w'; }();
+  if (use_ws && all_ou_pairs(a.P)) return launch_step_pairs(a);
   return launch_step(a);
 }
 
