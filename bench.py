@@ -177,17 +177,38 @@ def run_ours(args):
     acts = synth_actions(8, ENVS_PER_GPU, 1234 + rank, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    def one_step(i):
-        env = envs[i % slabs]
-        env.step(acts[i % len(acts)], auto_reset=True)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # Independent slabs are stepped round-robin on `--streams` CUDA streams, so that one slab's latency-bound
+    # step kernel (65,536 envs = 14 warps per SM) overlaps the previous slab's reset kernels.
+    n_str = max(1, min(args.streams, slabs))
+    streams = [torch.cuda.Stream(dev) for _ in range(n_str)]
+
+    def step_slab(i, acts_i):
+        env = envs[i % slabs]
+        with torch.cuda.stream(streams[i % n_str]):
+            env.step(acts_i)                                           # the fused step kernel (dominant kernel)
+            env._reset_launch(env.t["done"], WINDOW, True, None, None)  # masked auto-reset + history fill
+
+    def fork(ev):
+        for st in streams:
+            st.wait_event(ev)
+
+    def join():
+        for st in streams:
+            e_ = torch.cuda.Event()
+            e_.record(st)
+            stream.wait_event(e_)
+
+    ev_w = torch.cuda.Event()
+    ev_w.record(stream)
+    fork(ev_w)
     for i in range(W):
-        one_step(i)
+        step_slab(i, acts[i % len(acts)])
+    join()
     barrier()
 
     # ---- timed region 1: device-resident inputs ("value")
@@ -195,38 +216,62 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.3)
     launches0 = sum(e.launches for e in envs)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
+    fork(ev0)
+    t_issue = time.perf_counter()
     for i in range(K):
-        env = envs[(W + i) % slabs]
-        k_ev[i][0].record(stream)
-        env.step(acts[i % len(acts)])          # the fused step kernel (dominant kernel)
-        k_ev[i][1].record(stream)
-        env._reset_launch(env.t["done"], WINDOW, True, None, None)  # masked auto-reset + history fill
+        step_slab(W + i, acts[i % len(acts)])
+    t_issue = (time.perf_counter() - t_issue) / K * 1e3  # host time to enqueue one step (must stay below ms_per_step)
+    join()
     ev1.record(stream)
     barrier()
     launches = sum(e.launches for e in envs) - launches0
     ms_total = ev0.elapsed_time(ev1)
-    kern_ms = sum(a.elapsed_time(b) for a, b in k_ev) / K
     sampler.stop()
     clocks = sampler.summary()
 
-    # ---- timed region 2: end to end through the public API with HOST buffers ("e2e")
+    # ---- the dominant kernel alone (roofline): the step kernel of consecutive slabs back to back on ONE stream,
+    # CUDA events around every launch, resets outside the event pairs
+    KK = min(K, 200)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KK)]
+    for i in range(KK):
+        env = envs[(W + K + i) % slabs]
+        k_ev[i][0].record(stream)
+        env.step(acts[i % len(acts)])
+        k_ev[i][1].record(stream)
+        env._reset_launch(env.t["done"], WINDOW, True, None, None)
+    barrier()
+    kern_ms = sum(a.elapsed_time(b) for a, b in k_ev) / KK
+
+    # ---- timed region 2: end to end through the public API with HOST buffers ("e2e"): every step copies its
+    # (N,16) fp64 units from pinned host memory, runs step + auto-reset, and reads reward/done back to the host;
+    # the two streams let one slab's copies overlap the other's kernels
     host_acts = synth_actions(4, ENVS_PER_GPU, 999 + rank, pinned=True)
-    host_reward = torch.empty(ENVS_PER_GPU, dtype=torch.float64).pin_memory()
-    host_done = torch.empty(ENVS_PER_GPU, dtype=torch.bool).pin_memory()
+    host_reward = [torch.empty(ENVS_PER_GPU, dtype=torch.float64).pin_memory() for _ in range(n_str)]
+    host_done = [torch.empty(ENVS_PER_GPU, dtype=torch.bool).pin_memory() for _ in range(n_str)]
+
+    def e2e_step(i):
+        env = envs[i % slabs]
+        j = i % n_str
+        with torch.cuda.stream(streams[j]):
+            _s, r, d, _ = env.step(host_acts[i % 4], auto_reset=True)          # H2D of the units inside
+            host_reward[j].copy_(env.shaped_reward[0, :, 0], non_blocking=True)  # D2H of the step's result
+            host_done[j].copy_(d, non_blocking=True)
+
+    ev_w.record(stream)
+    fork(ev_w)
     for i in range(max(3, W // 2)):
-        _s, r, d, _ = envs[i % slabs].step(host_acts[i % 4], auto_reset=True)
-        host_reward.copy_(r, non_blocking=True)
+        e2e_step(i)
+    join()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    fork(e0)
     for i in range(K):
-        _s, r, d, _ = envs[i % slabs].step(host_acts[i % 4], auto_reset=True)   # H2D of units inside
-        host_reward.copy_(envs[i % slabs].shaped_reward[0, :, 0], non_blocking=True)  # D2H of the step's result
-        host_done.copy_(d, non_blocking=True)
+        e2e_step(i)
+    join()
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -260,7 +305,7 @@ def run_ours(args):
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": B * ENVS_PER_GPU},
             "e2e": {"value": world * ENVS_PER_GPU * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "host_issue_ms_per_step": t_issue, "clocks": clocks,
             "episode_stats": parallel.summarize_stats(stats, N_ASSETS),
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -324,6 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slabs", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

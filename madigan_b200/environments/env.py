@@ -60,13 +60,26 @@ class _View:
         return self._env.checkRisk(*a)
 
 
+import contextlib
+
+_NULL_CTX = contextlib.nullcontext()
+# raw cudaStream_t of torch's current stream on a device: the C accessor is ~10x cheaper than building a Stream object
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or \
+    (lambda idx: torch.cuda.current_stream(idx).cuda_stream)
+
 # reset workspaces are scratch (no state between calls): one per (device, stream), shared by all Envs
 _RESET_WS = {}
 
 
+_RESET_NEED = {}
+
+
 def _reset_workspace(lib_, P, n_envs, fill_ticks, device):
-    need = int(lib_.mdg_reset_workspace_bytes(C.byref(P), n_envs, fill_ticks))
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    nk = (P.n_normals, n_envs, fill_ticks)
+    need = _RESET_NEED.get(nk)
+    if need is None:
+        need = _RESET_NEED[nk] = int(lib_.mdg_reset_workspace_bytes(C.byref(P), n_envs, fill_ticks))
+    key = (device.index, _raw_stream(device.index))
     ws = _RESET_WS.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=device)
@@ -157,12 +170,34 @@ class Env:
             setattr(IO, name, self.t[name].data_ptr())
         self._IO = IO
         self._d = None
+        self._L = A.MdgLaunch(n_envs=N, env_offset=self.env_offset, seed=self.seed, window=k)
+        # zero-copy (N, nA) views of the [nA][N] output tensors, built once
+        t = self.t
+        self._resp = BrokerResponse("", t["timestamp"], t["trans_price"].t(), t["trans_units"].t(),
+                                    t["trans_cost"].t(), t["risk"].t(), t["margin_call"])
+        self._info = EnvInfo(self._resp, False)
+        self._states = [None] * k
+        self._want_multi, self._want_single = torch.Size((N, nA)), torch.Size((N,))
+        self._done_u8 = t["done"].view(torch.uint8)
 
     def _launch(self, mode=A.MODE_HOLD, asset_idx=0):
-        return A.MdgLaunch(n_envs=self.N, env_offset=self.env_offset, seed=self.seed, window=self.k,
-                           head=self.head, mode=mode, asset_idx=asset_idx,
-                           nstep_pos=self._gstep % self.R.nstep,
-                           stream=torch.cuda.current_stream(self.device).cuda_stream)
+        """The (persistent) launch descriptor, refreshed for this call: the host path of a step is a handful of
+        attribute writes and one ctypes call, so that Python can enqueue steps faster than the GPU retires them."""
+        L = self._L
+        L.head = self.head
+        L.mode = mode
+        L.asset_idx = asset_idx
+        L.nstep_pos = self._gstep % self.R.nstep
+        L.seed = self.seed
+        L.env_offset = self.env_offset
+        L.stream = _raw_stream(self.device.index)
+        return L
+
+    def _device_ctx(self):
+        """`with` context selecting this env's device only when it is not already current (saves ~5 us per call)."""
+        if torch.cuda.current_device() == self.device.index:
+            return _NULL_CTX
+        return torch.cuda.device(self.device)
 
     def _noise(self, normals, uniforms):
         keep = []
@@ -194,10 +229,16 @@ class Env:
     # ------------------------------------------------------------------ reset / step
     def _reset_launch(self, mask, fill_ticks, clear_nstep, normals, uniforms):
         io = self._IO
-        n_ptr, u_ptr, keep = self._noise(normals, uniforms)
-        io.normals, io.uniforms, io.units = n_ptr, u_ptr, None
+        if normals is None and uniforms is None:
+            io.normals = io.uniforms = None
+            keep = None
+        else:
+            io.normals, io.uniforms, keep = self._noise(normals, uniforms)
+        io.units = None
         m = None
-        if mask is not None:
+        if mask is self.t["done"]:
+            m = self._done_u8
+        elif mask is not None:
             m = torch.as_tensor(mask)
             if m.dtype == torch.bool:
                 m = m.view(torch.uint8)  # same bytes, no conversion kernel
@@ -214,9 +255,12 @@ class Env:
         del keep
 
     def _state(self):
-        t = self.t
-        return State(t["obs_price"][self.head].t(), t["obs_port"][self.head].t(), t["timestamp"],
-                     _ring=(self, self._version))
+        st = self._states[self.head]
+        if st is None:  # one State (views of ring slot `head`) per slot, built on first use
+            t = self.t
+            st = State(t["obs_price"][self.head].t(), t["obs_port"][self.head].t(), t["timestamp"], _ring=(self, 0))
+            self._states[self.head] = st
+        return st
 
     def reset(self, mask=None, fill_history=False, normals=None, uniforms=None):
         """Env::reset (Env.h:181-187).  ``mask``: (N,) bool/uint8, only those envs (None = all).
@@ -224,7 +268,7 @@ class Env:
         (reference: utils/preprocessor.py:191-194) so the whole window belongs to the new episode.
         Returns the newest State row."""
         fill = self.k if fill_history else 1
-        with torch.cuda.device(self.device):
+        with self._device_ctx():
             self._reset_launch(mask, fill, True, normals, uniforms)
         if mask is None:
             self.n_valid = fill
@@ -249,23 +293,28 @@ class Env:
         else:
             raise TypeError("step() takes at most (assetIdx, units)")
         io = self._IO
-        with torch.cuda.device(self.device):
+        with self._device_ctx():
             if units is not None:
-                u = torch.as_tensor(units, dtype=torch.float64)
-                want = (self.N, self.nA) if mode == A.MODE_MULTI else (self.N,)
-                if self.N == 1 and u.dim() == len(want) - 1:
-                    u = u.unsqueeze(0)
-                if tuple(u.shape) != want:
-                    raise ValueError(f"units must have shape {want}, got {tuple(u.shape)}")
-                if u.device != self.device or not u.is_contiguous():
+                u = units if (isinstance(units, torch.Tensor) and units.dtype == torch.float64) \
+                    else torch.as_tensor(units, dtype=torch.float64)
+                want = self._want_multi if mode == A.MODE_MULTI else self._want_single
+                if u.shape != want:
+                    if self.N == 1 and u.dim() == len(want) - 1:
+                        u = u.unsqueeze(0)
+                    if u.shape != want:
+                        raise ValueError(f"units must have shape {tuple(want)}, got {tuple(u.shape)}")
+                if not u.is_cuda or u.device != self.device or not u.is_contiguous():
                     dst = self.t["units"] if mode == A.MODE_MULTI else self.t["units"].view(-1)[:self.N]
                     dst.copy_(u, non_blocking=True)  # H2D from (pinned) host memory, async on this stream
                     u = dst
                 io.units = u.data_ptr()
             else:
                 io.units = None
-            n_ptr, u_ptr, keep = self._noise(normals, uniforms)
-            io.normals, io.uniforms = n_ptr, u_ptr
+            if normals is None and uniforms is None:
+                io.normals = io.uniforms = None
+                keep = None
+            else:
+                io.normals, io.uniforms, keep = self._noise(normals, uniforms)
             self.head = (self.head + 1) % self.k
             self.n_valid = min(self.k, self.n_valid + 1)
             L = self._launch(mode, asset_idx)
@@ -277,9 +326,7 @@ class Env:
             if auto_reset:
                 self._reset_launch(self.t["done"], self.k, True, None, None)
         t = self.t
-        resp = BrokerResponse("", t["timestamp"], t["trans_price"].t(), t["trans_units"].t(),
-                              t["trans_cost"].t(), t["risk"].t(), t["margin_call"])
-        return self._state(), t["reward"], t["done"], EnvInfo(resp, False)
+        return self._state(), t["reward"], t["done"], self._info
 
     # ------------------------------------------------------------------ in-kernel rewards
     @property
