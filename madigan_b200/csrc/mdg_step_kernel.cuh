@@ -344,6 +344,7 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
 }
 
 // after the tick of asset i: state/observation stores, fold of the new position value, reward stash
+template <int BS>
 __device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t N, int64_t e, int na, int i,
                                           double cur, double newp, double prev_val, double tp, double tu,
                                           double tc, double* st_cur, double* st_pm) {
@@ -352,8 +353,8 @@ __device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t
   const double cur_val = cur * newp;
   A.nav = (i == 0) ? cur_val : A.nav + cur_val;
   A.gsum += fabs(cur_val);
-  st_cur[(int64_t)i * kBlock] = cur_val;
-  st_pm[(int64_t)i * kBlock] = prev_val + (tu * tp + tc);  // prev_val + mar_diff, offpolicy_q.py:153-156
+  st_cur[(int64_t)i * BS] = cur_val;
+  st_pm[(int64_t)i * BS] = prev_val + (tu * tp + tc);  // prev_val + mar_diff, offpolicy_q.py:153-156
 }
 
 // in-order normal draws for the all-OU-pairs kernel: one Philox block = two normals (same (block, lane)
@@ -382,23 +383,26 @@ __device__ __forceinline__ double next_normal(NormalFifo& f, uint32_t gid, uint3
   return r * cs;
 }
 
-constexpr int kStepMinBlocks = 4;  // 512 threads / SM: <= 128 registers (no spills), 2*nA*8 B of shared memory per thread
-
-template <bool PAIRS>
-__global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __grid_constant__ StepArgs a) {
-  // per-thread stash, [2*nA][kBlock]: position value after the tick, and prev value + mar_diff
+// Two register budgets of the same kernel, chosen by the number of envs per launch (profiles/largeN.py):
+//   128 registers -> 4 blocks of 128 per SM: the 443 envs per SM of a 65,536-env launch are resident in ONE
+//     wave (that launch is latency-bound: a second wave would cost as much as the first);
+//   168 registers -> 3 blocks per SM, no spills: best throughput when there are many waves (>= 262,144 envs).
+// (64-thread blocks x 7 per SM at 144 registers were measured slower than either.)
+template <bool PAIRS, int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ StepArgs a) {
+  // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff
   extern __shared__ double stash[];
   const MdgParams& P = a.P;
   const MdgState& S = a.S;
   const int64_t N = a.L.n_envs;
   const int na = P.n_assets;
   const int tid = threadIdx.x;
-  const int64_t e = (int64_t)blockIdx.x * kBlock + tid;
+  const int64_t e = (int64_t)blockIdx.x * BS + tid;
   if (e >= N) return;
   const int mode = a.L.mode;
   const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
-  double* st_cur = stash + tid;                        // [j * kBlock]
-  double* st_pm = stash + (int64_t)na * kBlock + tid;  // [j * kBlock]
+  double* st_cur = stash + tid;                        // [j * BS]
+  double* st_pm = stash + (int64_t)na * BS + tid;  // [j * BS]
   const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;
 
   StepAcc A;
@@ -487,8 +491,8 @@ __global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __gr
       S.gstate[(int64_t)g0.gslot * N + e] = mean;
       const double newp0 = price[0] + ((g0.p[0] * (mean - price[0])) + mean * (z0 * g0.p[1]));
       const double newp1 = price[1] + ((g1.p[0] * (mean - price[1])) + mean * (z1 * g1.p[1]));
-      post_tick(a, A, N, e, na, 2 * p, cur[0], newp0, prev_val[0], tp[0], tu[0], tc[0], st_cur, st_pm);
-      post_tick(a, A, N, e, na, 2 * p + 1, cur[1], newp1, prev_val[1], tp[1], tu[1], tc[1], st_cur, st_pm);
+      post_tick<BS>(a, A, N, e, na, 2 * p, cur[0], newp0, prev_val[0], tp[0], tu[0], tc[0], st_cur, st_pm);
+      post_tick<BS>(a, A, N, e, na, 2 * p + 1, cur[1], newp1, prev_val[1], tp[1], tu[1], tc[1], st_cur, st_pm);
     }
   } else {
     // ---- generic path (Composite / sine / trend sources): one asset per iteration
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __gr
         double* gs = S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
         newp = gen_tick(g, price, gs, dr, pair_mean);
       }
-      post_tick(a, A, N, e, na, i, cur, newp, prev_val, tp, tu, tc, st_cur, st_pm);
+      post_tick<BS>(a, A, N, e, na, i, cur, newp, prev_val, tp, tu, tc, st_cur, st_pm);
     }
   }
 
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __gr
   double rsum = 0.;
 #pragma unroll 2
   for (int j = 0; j < na; ++j) {
-    const double cur_val = st_cur[(int64_t)j * kBlock];
+    const double cur_val = st_cur[(int64_t)j * BS];
     const double w = cur_val * inv_eq;
     a.IO.obs_port[((int64_t)head * (na + 1) + j + 1) * N + e] = w;
     if (cosine) {
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __gr
       cosv_pp = cosv_pp + w * w; cosv_qq = cosv_qq + dj * dj; cosv_pq = cosv_pq + w * dj;
     }
     if (shaping && !cosine) {  // agent reward (offpolicy_q.py:152-164); with the cosine shaper see below
-      double x = (cur_val - st_pm[(int64_t)j * kBlock]) * inv_prev;
+      double x = (cur_val - st_pm[(int64_t)j * BS]) * inv_prev;
       x += 1;
       const double r = fast_log((x != x) ? x : ((x < .35) ? .35 : x));
       if (a.R.reduce_rewards) {
@@ -597,7 +601,7 @@ __global__ void __launch_bounds__(kBlock, kStepMinBlocks) step_kernel(const __gr
     const double extra = a.R.cosine_temp * (cosv_pq / (sqrt(cosv_pp) * sqrt(cosv_qq)));
 #pragma unroll 1
     for (int j = 0; j < na; ++j) {
-      double x = (st_cur[(int64_t)j * kBlock] - st_pm[(int64_t)j * kBlock]) * inv_prev;
+      double x = (st_cur[(int64_t)j * BS] - st_pm[(int64_t)j * BS]) * inv_prev;
       x += 1;
       const double r = fast_log((x != x) ? x : ((x < .35) ? .35 : x));
       if (a.R.reduce_rewards) {
@@ -636,12 +640,17 @@ static inline bool all_ou_pairs(const MdgParams& P) {
 
 static inline int launch_step(const StepArgs& a) {
   const int64_t N = a.L.n_envs;
-  const unsigned grid = (unsigned)((N + kBlock - 1) / kBlock);
-  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * kBlock;
-  if (all_ou_pairs(a.P))
-    step_kernel<true><<<grid, kBlock, smem, (cudaStream_t)a.L.stream>>>(a);
-  else
-    step_kernel<false><<<grid, kBlock, smem, (cudaStream_t)a.L.stream>>>(a);
+  cudaStream_t st = (cudaStream_t)a.L.stream;
+  const bool pairs = all_ou_pairs(a.P);
+  const unsigned grid = (unsigned)((N + 127) / 128);
+  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
+  if (N <= 148 * 512 * 2) {  // up to two waves at 4 blocks per SM
+    if (pairs) step_kernel<true, 128, 4><<<grid, 128, smem, st>>>(a);
+    else step_kernel<false, 128, 4><<<grid, 128, smem, st>>>(a);
+  } else {
+    if (pairs) step_kernel<true, 128, 3><<<grid, 128, smem, st>>>(a);
+    else step_kernel<false, 128, 3><<<grid, 128, smem, st>>>(a);
+  }
   return cuda_err(cudaGetLastError(), "mdg_step launch");
 }
 
