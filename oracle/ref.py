@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE, NOT PRODUCT CODE: ctypes front-end of oracle/_ref/libmadigan_ref.so -- the REFERENCE's own
+C++ env (Env / Broker / Account / Portfolio / DataSource sources compiled unmodified, see oracle/ref_build.py).
+Only tests/, __graft_entry__ and bench.py's baseline legs may import this."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libmadigan_ref.so")
+_LIB = None
+
+SYNTH, OU, OUPAIR, MULTIPAIR = 0, 1, 2, 3
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.ref_env_create.restype = vp
+        L.ref_env_create.argtypes = [C.c_int, C.c_int, dp, C.c_double, C.c_uint]
+        L.ref_env_destroy.argtypes = [vp]
+        L.ref_env_set.argtypes = [vp] + [C.c_double] * 6
+        L.ref_env_next_normals.restype = C.c_int
+        L.ref_env_next_normals.argtypes = [vp, dp]
+        L.ref_env_reset.argtypes = [vp, dp, dp, C.POINTER(C.c_longlong)]
+        L.ref_env_step.argtypes = [vp, C.c_int, dp, C.c_int, dp, dp, C.POINTER(C.c_longlong), dp, ip, dp, dp, dp, ip, ip]
+        L.ref_env_accounting.argtypes = [vp, dp, dp, dp]
+        L.ref_env_run.restype = C.c_longlong
+        L.ref_env_run.argtypes = [vp, C.c_longlong, dp, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class RefEnv:
+    """One reference Env (madigan/environments/cpp/Env.h) with a re-seeded generator."""
+
+    def __init__(self, kind, n_assets, params, init_cash=1_000_000., seed=12345):
+        self.L = lib()
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self.n = 2 if kind == OUPAIR else int(n_assets)
+        self.h = self.L.ref_env_create(kind, int(n_assets), _dp(p), float(init_cash), int(seed))
+
+    def __del__(self):
+        try:
+            self.L.ref_env_destroy(self.h)
+        except Exception:
+            pass
+
+    def set(self, reqM, maintM, tc_rel=0., tc_abs=0., sl_rel=0., sl_abs=0.):
+        self.L.ref_env_set(self.h, reqM, maintM, tc_rel, tc_abs, sl_rel, sl_abs)
+
+    def next_normals(self):
+        z = np.zeros(64)
+        n = self.L.ref_env_next_normals(self.h, _dp(z))
+        return z[:n].copy()
+
+    def reset(self):
+        price, port, ts = np.zeros(self.n), np.zeros(self.n + 1), C.c_longlong()
+        self.L.ref_env_reset(self.h, _dp(price), _dp(port), C.byref(ts))
+        return dict(price=price, portfolio=port, timestamp=ts.value)
+
+    def step(self, units=None, asset_idx=None):
+        n = self.n
+        price, port, ts = np.zeros(n), np.zeros(n + 1), C.c_longlong()
+        reward, done, mc = C.c_double(), C.c_int(), C.c_int()
+        tp, tu, tc = np.zeros(n), np.zeros(n), np.zeros(n)
+        risk = np.zeros(n, dtype=np.int32)
+        if units is None:
+            mode, u, ai = 0, np.zeros(1), 0
+        elif asset_idx is not None:
+            mode, u, ai = 2, np.array([units], dtype=np.float64), int(asset_idx)
+        else:
+            mode, u, ai = 1, np.ascontiguousarray(units, dtype=np.float64), 0
+        self.L.ref_env_step(self.h, mode, _dp(u), ai, _dp(price), _dp(port), C.byref(ts), C.byref(reward),
+                            C.byref(done), _dp(tp), _dp(tu), _dp(tc), risk.ctypes.data_as(C.POINTER(C.c_int)),
+                            C.byref(mc))
+        return dict(price=price, portfolio=port, timestamp=ts.value, reward=reward.value, done=bool(done.value),
+                    transactionPrice=tp, transactionUnits=tu, transactionCost=tc, riskInfo=risk,
+                    marginCall=bool(mc.value))
+
+    def accounting(self):
+        out, led, mep = np.zeros(8), np.zeros(self.n), np.zeros(self.n)
+        self.L.ref_env_accounting(self.h, _dp(out), _dp(led), _dp(mep))
+        keys = ("equity", "cash", "pnl", "balance", "availableMargin", "usedMargin", "borrowedMargin",
+                "borrowedAssetValue")
+        d = dict(zip(keys, out))
+        d["ledger"], d["meanEntryPrices"] = led, mep
+        return d
+
+    def run(self, steps, acts):
+        """`steps` calls of Env::step(units) cycling over acts (n_act, nA), reset on done; returns #resets."""
+        a = np.ascontiguousarray(acts, dtype=np.float64)
+        return int(self.L.ref_env_run(self.h, int(steps), _dp(a), a.shape[0]))
