@@ -14,12 +14,19 @@
  *     a+u*(b-a), uniform_int(a,b) == a+floor(u*(b-a+1)); when no stream is given
  *     the draws come from Philox4x32-10 keyed by (seed, env id, tick, slot).
  *
- * PARITY STATUS: the ledger (Portfolio/Broker) is pinned by the reference's own
- * known-answer tests (environments/cpp/tests/envTest.py:102-566,
- * envTest.cpp:171-266), replayed in tests/test_oracle_ledger_kat.py.  The
- * generators other than noise-free Synth, Env::step's reward/done and non-zero
- * slippage/cost have no reference test: for those "parity unpinned" -- the cited
- * source lines are the only specification.
+ * PARITY STATUS: pinned.
+ *   - Ledger (Portfolio/Broker): the reference's own known-answer tests
+ *     (environments/cpp/tests/envTest.py:102-566, envTest.cpp:171-266), replayed in
+ *     tests/test_oracle_ledger_kat.py.
+ *   - Env::step end to end -- all nine generators (Synth, SawTooth, Triangle,
+ *     Gaussian, OU, OUPair, SimpleTrend, TrendOU, TrendyOU), reward clamp, done,
+ *     slippage/cost, risk gates under leverage, accounting properties: BIT-EXACT
+ *     against the reference's own C++ sources compiled here unmodified
+ *     (oracle/ref_build.py -> oracle/_ref, tests/test_oracle_vs_reference.py), with
+ *     the reference's <random> draws replayed into the injected stream.
+ *   - Shapers: the reference's own Python (tests/golden/shapers.npz).
+ *   - Not pinned: Composite's asset ORDER (the reference iterates an
+ *     unordered_map, DataSource.cpp:418-433; here: config insertion order).
  */
 #include "mdg_oracle.h"
 

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libmadigan_ref.so")
 _LIB = None
 
-SYNTH, OU, OUPAIR, MULTIPAIR = 0, 1, 2, 3
+SYNTH, OU, OUPAIR, MULTIPAIR, SIMPLETREND, TRENDOU, TRENDYOU, SAWTOOTH, TRIANGLE, GAUSSIAN = range(10)
 
 
 def available():
@@ -28,6 +28,9 @@ def lib():
         L.ref_env_set.argtypes = [vp] + [C.c_double] * 6
         L.ref_env_next_normals.restype = C.c_int
         L.ref_env_next_normals.argtypes = [vp, dp]
+        L.ref_env_next_draws.restype = C.c_int
+        L.ref_env_next_draws.argtypes = [vp, dp, dp, C.c_int]
+        L.ref_env_trend_state.argtypes = [vp, dp, ip, ip, ip]
         L.ref_env_reset.argtypes = [vp, dp, dp, C.POINTER(C.c_longlong)]
         L.ref_env_step.argtypes = [vp, C.c_int, dp, C.c_int, dp, dp, C.POINTER(C.c_longlong), dp, ip, dp, dp, dp, ip, ip]
         L.ref_env_accounting.argtypes = [vp, dp, dp, dp]
@@ -63,6 +66,20 @@ class RefEnv:
         z = np.zeros(64)
         n = self.L.ref_env_next_normals(self.h, _dp(z))
         return z[:n].copy()
+
+    def next_draws(self, after_reset=False):
+        """trend sources: (normals[n], uniforms[4n]) of the next getData(), in the oracle's slot order"""
+        z, u = np.zeros(self.n), np.zeros(4 * self.n)
+        n = self.L.ref_env_next_draws(self.h, _dp(z), _dp(u), int(after_reset))
+        assert n == self.n
+        return z, u
+
+    def trend_state(self):
+        ip = C.POINTER(C.c_int)
+        dY = np.zeros(self.n)
+        d, ln, tr = (np.zeros(self.n, dtype=np.int32) for _ in range(3))
+        self.L.ref_env_trend_state(self.h, _dp(dY), d.ctypes.data_as(ip), ln.ctypes.data_as(ip), tr.ctypes.data_as(ip))
+        return dict(dY=dY, direction=d, length=ln, trending=tr.astype(bool))
 
     def reset(self):
         price, port, ts = np.zeros(self.n), np.zeros(self.n + 1), C.c_longlong()

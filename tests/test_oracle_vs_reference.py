@@ -35,13 +35,18 @@ CASES = {
                                        dX=0.01, noise=0.05)),
     "ou": (ref.OU, "OU", dict(mean=[10., 5., 1., 2.], theta=[.08, .15, .15, .1], phi=[.04, .02, .01, .03])),
     "oupair": (ref.OUPAIR, "OUPair", dict(theta=.015, phi=.01, noise=.03)),
+    "sawtooth": (ref.SAWTOOTH, "SawTooth", dict(freq=[1., 0.3, 2.], mu=[2., 2.1, 2.2], amp=[1., 1.2, 1.3],
+                                                phase=[0., 1., 2.], dX=0.01, noise=0.05)),
+    "triangle": (ref.TRIANGLE, "Triangle", dict(freq=[1., 0.3, 2.], mu=[2., 2.1, 2.2], amp=[1., 1.2, 1.3],
+                                                phase=[0., 1., 2.], dX=0.01, noise=0.05)),
+    "gaussian": (ref.GAUSSIAN, "Gaussian", dict(mean=[2., 5., 10.], var=[.5, 1., 2.])),
     "pairs8": (ref.MULTIPAIR, "Composite", dict(theta=.015, phi=.01, noise=.03)),
 }
 
 
 def build(case, margins, costs, seed):
     kind, ds_type, cfg = CASES[case]
-    if kind == ref.SYNTH:
+    if kind in (ref.SYNTH, ref.SAWTOOTH, ref.TRIANGLE):
         n = len(cfg["freq"])
         p = [x for i in range(n) for x in (cfg["freq"][i], cfg["mu"][i], cfg["amp"][i], cfg["phase"][i])]
         p += [cfg["dX"], cfg["noise"]]
@@ -49,6 +54,10 @@ def build(case, margins, costs, seed):
     elif kind == ref.OU:
         n = len(cfg["mean"])
         p = [x for i in range(n) for x in (cfg["mean"][i], cfg["theta"][i], cfg["phi"][i])]
+        ds_cfg = cfg
+    elif kind == ref.GAUSSIAN:
+        n = len(cfg["mean"])
+        p = [x for i in range(n) for x in (cfg["mean"][i], cfg["var"][i])]
         ds_cfg = cfg
     elif kind == ref.OUPAIR:
         n, p, ds_cfg = 2, [cfg["theta"], cfg["phi"], cfg["noise"]], cfg
@@ -123,6 +132,78 @@ def test_env_step_bit_exact_vs_reference(case, margins, costs, scale):
             assert same(rs["price"], os_["price"]) and same(rs["portfolio"], os_["portfolio"])
     if margins[0] < 1.:
         assert A.RISK_INSUFF_MARGIN in seen
+
+
+TREND = dict(trend_prob=[.05, .1, .02], min_period=[3, 5, 10], max_period=[9, 30, 40],
+             dYMin=[.001, .02, .05], dYMax=[.01, .2, .6], start=[10., .5, 2.])
+TREND_CASES = {
+    "simpletrend": (ref.SIMPLETREND, "SimpleTrend", dict(TREND, noise=[.01, .05, .2])),
+    "trendou": (ref.TRENDOU, "TrendOU", dict(TREND, theta=[.1, .3, .05], phi=[.02, .1, .3], noise_trend=[.01, .05, .2],
+                                             ema_alpha=[.1, .2, .3])),
+    "trendyou": (ref.TRENDYOU, "TrendyOU", dict(TREND, theta=[.1, .3, .05], phi=[.02, .1, .3],
+                                                noise_trend=[.01, .05, .2], ema_alpha=[.1, .2, .3])),
+}
+
+
+def build_trend(case, seed):
+    kind, ds_type, cfg = TREND_CASES[case]
+    n = len(cfg["start"])
+    if kind == ref.SIMPLETREND:
+        keys = ("trend_prob", "min_period", "max_period", "noise", "start", "dYMin", "dYMax")
+    else:
+        keys = ("trend_prob", "min_period", "max_period", "dYMin", "dYMax", "start", "theta", "phi", "noise_trend",
+                "ema_alpha")
+    p = [float(cfg[k][i]) for i in range(n) for k in keys]
+    r = ref.RefEnv(kind, n, p, 1_000_000., seed)
+    r.set(.1, .25, .02, 0., .001, 0.)
+    P, _ = make_params(ds_type, cfg, required_margin=.1, maintenance_margin=.25, transaction_cost_rel=.02,
+                       slippage_rel=.001)
+    for i in range(n):
+        assert P.gen[i].nslot == i and P.gen[i].uslot == 4 * i
+    return r, OracleEnv(P, construct=False), n
+
+
+def oracle_trend_state(o, P_type, n):
+    """(dY, direction, length, trending) from the oracle's packed generator state"""
+    gs = np.ctypeslib.as_array(o.e.gstate)
+    per = {ref.SIMPLETREND: (2, 0, 1), ref.TRENDOU: (3, 1, 2), ref.TRENDYOU: (4, 2, 3)}[P_type]
+    dY = np.array([gs[per[0] * i + per[1]] for i in range(n)])
+    f = np.array([gs[per[0] * i + per[2]] for i in range(n)]).view(np.int64)
+    return dict(dY=dY, direction=np.where(f & 2, 1, -1), length=(f >> 32).astype(np.int32), trending=(f & 1) == 1)
+
+
+@pytest.mark.parametrize("case", list(TREND_CASES))
+@pytest.mark.parametrize("seed", [7, 4242])
+def test_trend_generators_bit_exact_vs_reference(case, seed):
+    """SimpleTrend / TrendOU / TrendyOU: data-dependent draw pattern (uniform test, direction, integer trend
+    length, dY), floors at 0.01 / 0.1 and direction flips -- prices and the trend state machine bit for bit."""
+    kind = TREND_CASES[case][0]
+    rng = np.random.default_rng(seed)
+    r, o, n = build_trend(case, seed)
+    z, u = r.next_draws(after_reset=True)
+    rs, os_ = r.reset(), o.reset(normals=z, uniforms=u)
+    assert same(rs["price"], os_["price"])
+    n_trending, dones, floors = 0, 0, 0
+    for t in range(3000):
+        z, u = r.next_draws()
+        units = gen_units(rng, o, n, 60_000.) if t % 5 else None
+        ro, oo = r.step(units), o.step(units, normals=z, uniforms=u)
+        assert same(ro["price"], oo["price"]), f"step {t}: {ro['price']} vs {oo['price']}"
+        assert same(ro["portfolio"], oo["portfolio"]) and same(ro["reward"], oo["reward"]), f"step {t}"
+        assert ro["done"] == oo["done"]
+        a, b = r.trend_state(), oracle_trend_state(o, kind, n)
+        assert np.array_equal(a["trending"], b["trending"]), f"step {t}"
+        assert same(a["dY"], b["dY"]), f"step {t}"
+        live = a["trending"]
+        assert np.array_equal(a["length"][live], b["length"][live]), f"step {t}"
+        n_trending += int(live.sum())
+        floors += int((ro["price"] <= .1001).sum())
+        if oo["done"]:
+            dones += 1
+            z, u = r.next_draws(after_reset=True)
+            rs, os_ = r.reset(), o.reset(normals=z, uniforms=u)
+            assert same(rs["price"], os_["price"])
+    assert n_trending > 200
 
 
 def test_reference_timestamp_counts_ticks():
