@@ -524,12 +524,15 @@ extern "C" int mdg_reset_ws(const MdgParams* P, const MdgState* S, const MdgStep
   reset_scan_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(a);
   const int passes = (int)((N + a.cap - 1) / a.cap);
   const int nb = (P->n_normals + 1) / 2 > 0 ? (P->n_normals + 1) / 2 : 1;
-  for (int p = 0; p < passes; ++p) {
+  // profiling knob (profiles/breakdown.py): stop after the scan (1) or the rng kernel (2); results are then wrong
+  static const int phases = [] { const char* v = getenv("MDG_RESET_PHASES"); return v ? atoi(v) : 3; }();
+  for (int p = 0; p < passes && phases >= 2; ++p) {
     a.pass = p;
     // grids sized for a full pass but capped: the kernels are grid-stride and exit at once past the list end
     unsigned g1 = (unsigned)(a.cap < 148 * 8 ? a.cap : 148 * 8);  // one block per listed env, grid-stride
     (void)nb;
     reset_rng_kernel<<<g1 ? g1 : 1, 256, 0, st>>>(a);
+    if (phases < 3) continue;
     int64_t rec_items = (int64_t)a.cap * P->n_assets;
     unsigned g2 = (unsigned)((rec_items + 127) / 128 < 148 * 16 ? (rec_items + 127) / 128 : 148 * 16);
     reset_recur_kernel<<<g2 ? g2 : 1, 128, 0, st>>>(a);

@@ -155,15 +155,21 @@ static __device__ __noinline__ double shaper_pop(const MdgReward& R, const NStep
 // ReplayBuffer.add (replay_buffer.py:68-80) + NStepBuffer.pop_nstep_sarsd (nstep_buffer.py:342-361)
 // for component c of env e: add `raw`, pop once when full, drain on done.
 static __device__ __noinline__ void shaper_add(const StepArgs& a, int64_t e, int c, int ra, double raw, bool done,
-                                           int len_before, int& len_after, int& n_popped) {
+                                           int len_before, int& len_after, int& n_popped,
+                                           const double* pre_ab = nullptr, int pre_stride = 0) {
   const MdgReward& R = a.R;
   const int64_t N = a.L.n_envs;
   const int n = R.nstep;
   double A = 0., B = 0.;
   const bool moments = (R.shaper == MDG_SHAPER_DSR || R.shaper == MDG_SHAPER_DDR);
   if (moments) {
-    A = a.S.shaper_A[(int64_t)c * N + e];
-    B = a.S.shaper_B[(int64_t)c * N + e];
+    if (pre_ab && c == 0) {  // component 0 was prefetched into shared memory at kernel start
+      A = pre_ab[0];
+      B = pre_ab[pre_stride];
+    } else {
+      A = a.S.shaper_A[(int64_t)c * N + e];
+      B = a.S.shaper_B[(int64_t)c * N + e];
+    }
   }
   NStepView v;
   v.ring = a.S.nstep_ring;
@@ -343,44 +349,62 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
   A.gsum += fabs(t_ml) + fabs(bm);
 }
 
+// Asynchronous global -> shared copies (LDGSTS): the next pairs' state is prefetched without holding registers.
+// (At the 128-register budget the compiler spilled register prefetches to local memory right after the load --
+// a store that waits for the load -- which made the prefetch a stall; profiles/r1_notes.md.)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory");
+}
+// prefetch rows of one pair: price, ledger, mean_entry, borrowed, units (x2 each), shared mean
+constexpr int kPfRows = 11;
+constexpr int kPfStages = 2;
+// dynamic shared memory of the all-pairs kernel, in rows of BS doubles:
+//   [0, 2 nA) stash | [2 nA, 2 nA + 22) prefetch stages      (54 rows at nA 16: four blocks per SM fit in 228 KB)
+static inline size_t pairs_smem_bytes(int na, int bs) { return sizeof(double) * (size_t)(2 * na + kPfRows * kPfStages) * bs; }
+
+// Shared-memory stash of the all-OU-pairs kernel, one column per thread, four rows per pair p:
+//   before the pair is processed: rows 4p..4p+2 hold its three normals (noise slots 3p..3p+2);
+//   afterwards: rows 4p, 4p+1 = position values after the tick, rows 4p+2, 4p+3 = prev value + mar_diff.
+__device__ __forceinline__ int stash_normal_row(int slot) { const int p = slot / 3; return 4 * p + (slot - 3 * p); }
+template <bool PAIRS> __device__ __forceinline__ int stash_cur_row(int j, int na) {
+  return PAIRS ? 4 * (j >> 1) + (j & 1) : j;
+}
+template <bool PAIRS> __device__ __forceinline__ int stash_pm_row(int j, int na) {
+  return PAIRS ? 4 * (j >> 1) + 2 + (j & 1) : na + j;
+}
+
 // after the tick of asset i: state/observation stores, fold of the new position value, reward stash
-template <int BS>
+template <bool PAIRS, int BS>
 __device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t N, int64_t e, int na, int i,
                                           double cur, double newp, double prev_val, double tp, double tu,
-                                          double tc, double* st_cur, double* st_pm) {
+                                          double tc, double* st) {
   a.S.price[(int64_t)i * N + e] = newp;
   a.IO.obs_price[((int64_t)a.L.head * na + i) * N + e] = newp;  // State.price row (Env.h:202,228,254)
   const double cur_val = cur * newp;
   A.nav = (i == 0) ? cur_val : A.nav + cur_val;
   A.gsum += fabs(cur_val);
-  st_cur[(int64_t)i * BS] = cur_val;
-  st_pm[(int64_t)i * BS] = prev_val + (tu * tp + tc);  // prev_val + mar_diff, offpolicy_q.py:153-156
+  st[stash_cur_row<PAIRS>(i, na) * BS] = cur_val;
+  st[stash_pm_row<PAIRS>(i, na) * BS] = prev_val + (tu * tp + tc);  // prev_val + mar_diff, offpolicy_q.py:153-156
 }
 
-// in-order normal draws for the all-OU-pairs kernel: one Philox block = two normals (same (block, lane)
-// addressing as draw_normal: slot s -> block s>>1, lane s&1; slots are consumed in increasing order)
-struct NormalFifo {
-  double zb;     // lane 1 of the current block, not yet consumed
-  int have;      // 1 if zb is valid
-  uint32_t blk;  // next Philox block
-};
-__device__ __forceinline__ double next_normal(NormalFifo& f, uint32_t gid, uint32_t t_lo, uint32_t t_hi,
-                                              uint32_t k0, uint32_t k1) {
-  if (f.have) {
-    f.have = 0;
-    return f.zb;
-  }
+// One Philox block -> two standard normals (Box-Muller), the same (block, lane) addressing as draw_normal:
+// slot s = block s>>1, lane s&1.
+__device__ __forceinline__ void normal_block(uint32_t gid, uint32_t blk, uint32_t t_lo, uint32_t t_hi, uint32_t k0,
+                                             uint32_t k1, double& z_lane0, double& z_lane1) {
   uint64_t x0, x1;
-  philox4x32_10(gid, f.blk, t_lo, t_hi, k0, k1, x0, x1);
-  f.blk += 1;
+  philox4x32_10(gid, blk, t_lo, t_hi, k0, k1, x0, x1);
   const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
   const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
   const double r = sqrt(-2.0 * fast_log_pos(u1));
   double sn, cs;
   fast_sincos_2pi(u2, sn, cs);
-  f.zb = r * sn;
-  f.have = 1;
-  return r * cs;
+  z_lane0 = r * cs;
+  z_lane1 = r * sn;
 }
 
 // Two register budgets of the same kernel, chosen by the number of envs per launch (profiles/largeN.py):
@@ -390,7 +414,8 @@ __device__ __forceinline__ double next_normal(NormalFifo& f, uint32_t gid, uint3
 // (64-thread blocks x 7 per SM at 144 registers were measured slower than either.)
 template <bool PAIRS, int BS, int MINB>
 __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ StepArgs a) {
-  // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff
+  // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff (and, in the
+  // all-pairs kernel, this step's normals before they are consumed; see stash_normal_row)
   extern __shared__ double stash[];
   const MdgParams& P = a.P;
   const MdgState& S = a.S;
@@ -401,9 +426,54 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
   if (e >= N) return;
   const int mode = a.L.mode;
   const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
-  double* st_cur = stash + tid;                        // [j * BS]
-  double* st_pm = stash + (int64_t)na * BS + tid;  // [j * BS]
+  double* st = stash + tid;  // this thread's column, [row * BS]
   const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;
+  const bool moments = shaping && (a.R.shaper == MDG_SHAPER_DSR || a.R.shaper == MDG_SHAPER_DDR);
+  double* pf = st + (int64_t)2 * na * BS;                     // prefetch stages (all-pairs kernel only)
+  const double* pre_ab = nullptr;
+#ifndef MDG_PF
+#define MDG_PF 1
+#endif
+  auto prefetch_hint = [&](int pp) {
+    const int64_t o0 = (int64_t)(2 * pp) * N + e, o1 = o0 + N;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.price + o0));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.price + o1));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.ledger + o0));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.ledger + o1));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.mean_entry + o0));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.mean_entry + o1));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.borrowed + o0));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.borrowed + o1));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e));
+  };
+  auto prefetch_pair = [&](int pp) {
+    double* d = pf + (int64_t)(pp & 1) * (kPfRows * BS);
+    const int64_t o0 = (int64_t)(2 * pp) * N + e, o1 = o0 + N;
+    cp_async8(d + 0 * BS, S.price + o0);      cp_async8(d + 1 * BS, S.price + o1);
+    cp_async8(d + 2 * BS, S.ledger + o0);     cp_async8(d + 3 * BS, S.ledger + o1);
+    cp_async8(d + 4 * BS, S.mean_entry + o0); cp_async8(d + 5 * BS, S.mean_entry + o1);
+    cp_async8(d + 6 * BS, S.borrowed + o0);   cp_async8(d + 7 * BS, S.borrowed + o1);
+    if (mode == MDG_MODE_MULTI) { cp_async8(d + 8 * BS, urow + 2 * pp); cp_async8(d + 9 * BS, urow + 2 * pp + 1); }
+    cp_async8(d + 10 * BS, S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e);
+  };
+  if (PAIRS && MDG_PF == 1) {
+    prefetch_hint(0);
+    if (mode == MDG_MODE_MULTI) asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
+    if (moments) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_A + e));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_B + e));
+    }
+  }
+  if (PAIRS && MDG_PF == 0) {  // pairs 0 and 1 (and the shaper moments) start loading before anything else
+    prefetch_pair(0);
+    if (moments) {  // read at the very end of the kernel: pull the lines into L2 now
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_A + e));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_B + e));
+    }
+    cp_async_commit();
+    if (na > 2) prefetch_pair(1);
+    cp_async_commit();
+  }
 
   StepAcc A;
   A.cash = S.cash[e];
@@ -434,38 +504,45 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
     // ---- headline path: every asset belongs to an OU pair.  One iteration = one pair; the next pair's
     // state and units are loaded while the current pair is processed (software prefetch).
     const int np = na >> 1;
-    NormalFifo fifo;
-    fifo.zb = 0.; fifo.have = 0; fifo.blk = 0;
-    double n_price[2], n_cur[2], n_mep[2], n_bm[2], n_units[2], n_mean;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      n_price[q] = S.price[(int64_t)q * N + e];
-      n_cur[q] = S.ledger[(int64_t)q * N + e];
-      n_mep[q] = S.mean_entry[(int64_t)q * N + e];
-      n_bm[q] = S.borrowed[(int64_t)q * N + e];
-      n_units[q] = (mode == MDG_MODE_MULTI) ? urow[q] : 0.;
+    // This step's normals, all at once: the Philox + Box-Muller blocks are independent of each other and of
+    // the ledger, so they are generated four at a time (four interleaved dependency chains per thread --
+    // the kernel is latency-bound at one thread per env) while the first loads are in flight.
+    if (!a.IO.normals) {
+      const int nslots = 3 * np, nblk = (nslots + 1) >> 1;
+#pragma unroll 4
+      for (int b = 0; b < nblk; ++b) {
+        double za, zb;
+        normal_block(gid, (uint32_t)b, t_lo, t_hi, k0, k1, za, zb);
+        st[stash_normal_row(2 * b) * BS] = za;
+        if (2 * b + 1 < nslots) st[stash_normal_row(2 * b + 1) * BS] = zb;
+      }
     }
-    n_mean = S.gstate[(int64_t)P.gen[0].gslot * N + e];
 #pragma unroll 1
     for (int p = 0; p < np; ++p) {
       double price[2], cur[2], mep[2], bm[2], units[2], prev_val[2], tp[2], tu[2], tc[2];
       int risk[2];
-      double mean = n_mean;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        price[q] = n_price[q]; cur[q] = n_cur[q]; mep[q] = n_mep[q]; bm[q] = n_bm[q]; units[q] = n_units[q];
-      }
-      if (p + 1 < np) {
+      // the pair's state arrived through the prefetch stage p & 1 (group p; at most group p+1 is still in flight)
+      double mean;
+      if (MDG_PF == 0) {
+        cp_async_wait<1>();
+        const double* d = pf + (int64_t)(p & 1) * (kPfRows * BS);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const int j = 2 * p + 2 + q;
-          n_price[q] = S.price[(int64_t)j * N + e];
-          n_cur[q] = S.ledger[(int64_t)j * N + e];
-          n_mep[q] = S.mean_entry[(int64_t)j * N + e];
-          n_bm[q] = S.borrowed[(int64_t)j * N + e];
-          n_units[q] = (mode == MDG_MODE_MULTI) ? urow[j] : 0.;
+          price[q] = d[(0 + q) * BS]; cur[q] = d[(2 + q) * BS]; mep[q] = d[(4 + q) * BS]; bm[q] = d[(6 + q) * BS];
+          units[q] = (mode == MDG_MODE_MULTI) ? d[(8 + q) * BS] : 0.;
         }
-        n_mean = S.gstate[(int64_t)P.gen[2 * p + 2].gslot * N + e];
+        mean = d[10 * BS];
+      } else {
+        // plain loads of the current pair: their lines were pulled into L1 one iteration ago (no registers held
+        // across the iteration, so nothing to spill), then the hints for the next pair
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int64_t o = (int64_t)(2 * p + q) * N + e;
+          price[q] = S.price[o]; cur[q] = S.ledger[o]; mep[q] = S.mean_entry[o]; bm[q] = S.borrowed[o];
+          units[q] = (mode == MDG_MODE_MULTI) ? urow[2 * p + q] : 0.;
+        }
+        mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
+        if (p + 1 < np) prefetch_hint(p + 1);
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -483,16 +560,22 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
         z0 = a.IO.normals[(int64_t)g0.nslot * N + e];
         z1 = a.IO.normals[(int64_t)g1.nslot * N + e];
       } else {
-        z_rw = next_normal(fifo, gid, t_lo, t_hi, k0, k1);
-        z0 = next_normal(fifo, gid, t_lo, t_hi, k0, k1);
-        z1 = next_normal(fifo, gid, t_lo, t_hi, k0, k1);
+        z_rw = st[(4 * p) * BS];
+        z0 = st[(4 * p + 1) * BS];
+        z1 = st[(4 * p + 2) * BS];
       }
       mean += mean * (z_rw * g0.p[2]);
       S.gstate[(int64_t)g0.gslot * N + e] = mean;
+      // every value of stage p & 1 has been consumed: refill it with pair p + 2 (one group per iteration, possibly
+      // empty, so that wait_group 1 above always means "this pair has landed")
+      if (MDG_PF == 0) {
+        if (p + 2 < np) prefetch_pair(p + 2);
+        cp_async_commit();
+      }
       const double newp0 = price[0] + ((g0.p[0] * (mean - price[0])) + mean * (z0 * g0.p[1]));
       const double newp1 = price[1] + ((g1.p[0] * (mean - price[1])) + mean * (z1 * g1.p[1]));
-      post_tick<BS>(a, A, N, e, na, 2 * p, cur[0], newp0, prev_val[0], tp[0], tu[0], tc[0], st_cur, st_pm);
-      post_tick<BS>(a, A, N, e, na, 2 * p + 1, cur[1], newp1, prev_val[1], tp[1], tu[1], tc[1], st_cur, st_pm);
+      post_tick<true, BS>(a, A, N, e, na, 2 * p, cur[0], newp0, prev_val[0], tp[0], tu[0], tc[0], st);
+      post_tick<true, BS>(a, A, N, e, na, 2 * p + 1, cur[1], newp1, prev_val[1], tp[1], tu[1], tc[1], st);
     }
   } else {
     // ---- generic path (Composite / sine / trend sources): one asset per iteration
@@ -532,7 +615,7 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
         double* gs = S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
         newp = gen_tick(g, price, gs, dr, pair_mean);
       }
-      post_tick<BS>(a, A, N, e, na, i, cur, newp, prev_val, tp, tu, tc, st_cur, st_pm);
+      post_tick<false, BS>(a, A, N, e, na, i, cur, newp, prev_val, tp, tu, tc, st);
     }
   }
 
@@ -578,7 +661,7 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
   double rsum = 0.;
 #pragma unroll 2
   for (int j = 0; j < na; ++j) {
-    const double cur_val = st_cur[(int64_t)j * BS];
+    const double cur_val = st[stash_cur_row<PAIRS>(j, na) * BS];
     const double w = cur_val * inv_eq;
     a.IO.obs_port[((int64_t)head * (na + 1) + j + 1) * N + e] = w;
     if (cosine) {
@@ -586,14 +669,14 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
       cosv_pp = cosv_pp + w * w; cosv_qq = cosv_qq + dj * dj; cosv_pq = cosv_pq + w * dj;
     }
     if (shaping && !cosine) {  // agent reward (offpolicy_q.py:152-164); with the cosine shaper see below
-      double x = (cur_val - st_pm[(int64_t)j * BS]) * inv_prev;
+      double x = (cur_val - st[stash_pm_row<PAIRS>(j, na) * BS]) * inv_prev;
       x += 1;
       const double r = fast_log((x != x) ? x : ((x < .35) ? .35 : x));
       if (a.R.reduce_rewards) {
         rsum = (j == 0) ? r : rsum + r;
       } else {
         a.IO.agent_reward[(int64_t)j * N + e] = r;
-        shaper_add(a, e, j, ra, r, done, len_before, len_after, n_popped);
+        shaper_add(a, e, j, ra, r, done, len_before, len_after, n_popped, PAIRS ? pre_ab : nullptr, BS);
       }
     }
   }
@@ -601,23 +684,23 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
     const double extra = a.R.cosine_temp * (cosv_pq / (sqrt(cosv_pp) * sqrt(cosv_qq)));
 #pragma unroll 1
     for (int j = 0; j < na; ++j) {
-      double x = (st_cur[(int64_t)j * BS] - st_pm[(int64_t)j * BS]) * inv_prev;
+      double x = (st[stash_cur_row<PAIRS>(j, na) * BS] - st[stash_pm_row<PAIRS>(j, na) * BS]) * inv_prev;
       x += 1;
       const double r = fast_log((x != x) ? x : ((x < .35) ? .35 : x));
       if (a.R.reduce_rewards) {
         rsum = (j == 0) ? r : rsum + r;
       } else {
         a.IO.agent_reward[(int64_t)j * N + e] = r;
-        shaper_add(a, e, j, ra, r + extra, done, len_before, len_after, n_popped);
+        shaper_add(a, e, j, ra, r + extra, done, len_before, len_after, n_popped, PAIRS ? pre_ab : nullptr, BS);
       }
     }
     if (a.R.reduce_rewards) {
       a.IO.agent_reward[e] = rsum;
-      shaper_add(a, e, 0, 1, rsum + extra, done, len_before, len_after, n_popped);
+      shaper_add(a, e, 0, 1, rsum + extra, done, len_before, len_after, n_popped, PAIRS ? pre_ab : nullptr, BS);
     }
   } else if (shaping && a.R.reduce_rewards) {
     a.IO.agent_reward[e] = rsum;
-    shaper_add(a, e, 0, 1, rsum, done, len_before, len_after, n_popped);
+    shaper_add(a, e, 0, 1, rsum, done, len_before, len_after, n_popped, PAIRS ? pre_ab : nullptr, BS);
   }
   if (shaping) {
     if (a.R.nstep > 1) S.nstep_len[e] = len_after;
@@ -643,7 +726,18 @@ static inline int launch_step(const StepArgs& a) {
   cudaStream_t st = (cudaStream_t)a.L.stream;
   const bool pairs = all_ou_pairs(a.P);
   const unsigned grid = (unsigned)((N + 127) / 128);
-  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
+  const size_t smem = (pairs && MDG_PF == 0) ? pairs_smem_bytes(a.P.n_assets, 128) : sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
+  static const bool attr_set = [] {  // the all-pairs kernel uses up to 58 KB per block: four blocks fill the SM's 228 KB
+    const int maxb = (int)pairs_smem_bytes(MDG_MAX_ASSETS, 128);
+    cudaFuncSetAttribute(step_kernel<true, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(step_kernel<true, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    if (MDG_PF == 0) {
+      cudaFuncSetAttribute(step_kernel<true, 128, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(step_kernel<true, 128, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
+    return true;
+  }();
+  (void)attr_set;
   if (N <= 148 * 512 * 2) {  // up to two waves at 4 blocks per SM
     if (pairs) step_kernel<true, 128, 4><<<grid, 128, smem, st>>>(a);
     else step_kernel<false, 128, 4><<<grid, 128, smem, st>>>(a);
