@@ -9,7 +9,8 @@ import os
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmadigan_b200.so")
+_VARIANT = os.environ.get("MDG_LIB_VARIANT", "")  # profiling only, see build.py
+LIB_PATH = os.path.join(_HERE, f"libmadigan_b200.{_VARIANT}.so" if _VARIANT else "libmadigan_b200.so")
 _lib = None
 
 

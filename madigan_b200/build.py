@@ -15,9 +15,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libmadigan_b200.so")
-CAPS = (1, 2, 4, 8, 16)
+# MDG_LIB_VARIANT=<name> (profiling only): build/load libmadigan_b200.<name>.so next to the product library, so
+# that one GPU session can time several MDG_EXTRA_NVCC_FLAGS variants of a kernel side by side
+_VARIANT = os.environ.get("MDG_LIB_VARIANT", "")
+OBJ = os.path.join(HERE, "csrc", "_obj", _VARIANT) if _VARIANT else os.path.join(HERE, "csrc", "_obj")
+LIB = os.path.join(HERE, f"libmadigan_b200.{_VARIANT}.so" if _VARIANT else "libmadigan_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

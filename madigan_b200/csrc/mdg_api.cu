@@ -1,7 +1,7 @@
 // extern "C" entry points of the step path + the (rare, non-unrolled) reset / init kernels.
 #include <stdlib.h>
 
-#include "mdg_step_pairs.cuh"
+#include "mdg_step_kernel.cuh"
 
 namespace mdg {
 
@@ -456,12 +456,6 @@ extern "C" int mdg_step(const MdgParams* P, const MdgReward* R, const MdgState* 
       return set_err(MDG_E_INVALID, "nstep>1 needs nstep_ring/nstep_len");
     if (L->nstep_pos < 0 || L->nstep_pos >= a.R.nstep) return set_err(MDG_E_INVALID, "bad nstep_pos");
   }
-  const int na = P->n_assets;
-  (void)na;
-  // MDG_STEP_KERNEL=ws selects the warp-specialised experiment (mdg_step_pairs.cuh) for all-OU-pairs
-  // configurations; measured slower than the streaming kernel (profiles/r1_notes.md), so it is opt-in.
-  static const bool use_ws = [] { const char* v = getenv("MDG_STEP_KERNEL"); return v && v[0] == 'w'; }();
-  if (use_ws && all_ou_pairs(a.P)) return launch_step_pairs(a);
   return launch_step(a);
 }
 

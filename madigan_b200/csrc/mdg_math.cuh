@@ -38,6 +38,15 @@ __device__ __forceinline__ double fast_log_pos(double x) {
   const double f = m - 1.0;
   const double s = f * fast_rcp(2.0 + f);
   const double z = s * s;
+#ifdef MDG_ESTRIN
+  // Estrin's scheme: depth 4 instead of 8 dependent fma
+  const double z2 = z * z, z4 = z2 * z2;
+  const double a0 = fma(2.0 / 5.0, z, 2.0 / 3.0), a1 = fma(2.0 / 9.0, z, 2.0 / 7.0);
+  const double a2 = fma(2.0 / 13.0, z, 2.0 / 11.0), a3 = fma(2.0 / 17.0, z, 2.0 / 15.0);
+  const double b0 = fma(a1, z2, a0), b1 = fma(a3, z2, a2);
+  double p = fma(b1, z4, b0);
+  p = fma((2.0 / 19.0) * z4, z4, p);
+#else
   double p = 2.0 / 19.0;
   p = fma(p, z, 2.0 / 17.0);
   p = fma(p, z, 2.0 / 15.0);
@@ -47,6 +56,7 @@ __device__ __forceinline__ double fast_log_pos(double x) {
   p = fma(p, z, 2.0 / 7.0);
   p = fma(p, z, 2.0 / 5.0);
   p = fma(p, z, 2.0 / 3.0);
+#endif
   const double logm = fma(s * z, p, 2.0 * s);
   const double de = (double)e;
   // ln2 split so that e*ln2_hi is exact for |e| < 2^11

@@ -23,9 +23,35 @@ struct StepArgs {
   MdgState S;
   MdgStepIO IO;
   MdgLaunch L;
+  int units_v2;  // set by launch_step: the units matrix can be read with 16-byte loads (aligned base, even nA)
 };
 
 constexpr int kBlock = 128;
+
+// experiment knobs (MDG_EXTRA_NVCC_FLAGS + MDG_LIB_VARIANT, see build.py); the defaults are the measured best
+#ifndef MDG_PFDIST
+#define MDG_PFDIST 1    // prefetch distance in pairs
+#endif
+#ifndef MDG_RNG_UNROLL
+#define MDG_RNG_UNROLL 4
+#endif
+#ifndef MDG_TAIL_UNROLL
+#define MDG_TAIL_UNROLL 2
+#endif
+#ifndef MDG_UNITS_CG
+#define MDG_UNITS_CG 0  // 1: units read as 16-byte vectors that bypass L1 (measured slower at 65,536 envs)
+#endif
+#ifndef MDG_ST
+#define MDG_ST 0        // 0: plain stores, 1: st.global.cg (no L1 allocation) for state and outputs
+#endif
+#ifndef MDG_AB_L1
+#define MDG_AB_L1 0
+#endif
+constexpr int kRngUnroll = MDG_RNG_UNROLL, kTailUnroll = MDG_TAIL_UNROLL;  // #pragma unroll does not expand macros
+
+template <class T> __device__ __forceinline__ void gst(T* p, T v) {
+  if (MDG_ST) __stcg(p, v); else *p = v;
+}
 
 // ---------------------------------------------------------------------------
 // reward shapers (utils/buffers/nstep_buffer.py), one scalar component
@@ -155,21 +181,15 @@ static __device__ __noinline__ double shaper_pop(const MdgReward& R, const NStep
 // ReplayBuffer.add (replay_buffer.py:68-80) + NStepBuffer.pop_nstep_sarsd (nstep_buffer.py:342-361)
 // for component c of env e: add `raw`, pop once when full, drain on done.
 static __device__ __noinline__ void shaper_add(const StepArgs& a, int64_t e, int c, int ra, double raw, bool done,
-                                           int len_before, int& len_after, int& n_popped,
-                                           const double* pre_ab = nullptr, int pre_stride = 0) {
+                                           int len_before, int& len_after, int& n_popped) {
   const MdgReward& R = a.R;
   const int64_t N = a.L.n_envs;
   const int n = R.nstep;
   double A = 0., B = 0.;
   const bool moments = (R.shaper == MDG_SHAPER_DSR || R.shaper == MDG_SHAPER_DDR);
   if (moments) {
-    if (pre_ab && c == 0) {  // component 0 was prefetched into shared memory at kernel start
-      A = pre_ab[0];
-      B = pre_ab[pre_stride];
-    } else {
-      A = a.S.shaper_A[(int64_t)c * N + e];
-      B = a.S.shaper_B[(int64_t)c * N + e];
-    }
+    A = a.S.shaper_A[(int64_t)c * N + e];
+    B = a.S.shaper_B[(int64_t)c * N + e];
   }
   NStepView v;
   v.ring = a.S.nstep_ring;
@@ -320,9 +340,9 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
         if (bm > 0.) { A.cash -= bm; bm = 0.; }
       }
       if (bm < 0.) { A.cash -= bm; bm = 0.; }
-      S.ledger[(int64_t)i * N + e] = cur;
-      S.mean_entry[(int64_t)i * N + e] = mep;
-      S.borrowed[(int64_t)i * N + e] = bm;
+      gst(&S.ledger[(int64_t)i * N + e], cur);
+      gst(&S.mean_entry[(int64_t)i * N + e], mep);
+      gst(&S.borrowed[(int64_t)i * N + e], bm);
       // running sums and their magnitude bound
       const double n_av = cur * price, n_ml = mep * cur;
       A.rAV += n_av - prev_val;
@@ -336,9 +356,9 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
     }
   }
   if (a.L.mode != MDG_MODE_HOLD) {
-    a.IO.trans_price[(int64_t)i * N + e] = tp;
-    a.IO.trans_units[(int64_t)i * N + e] = tu;
-    a.IO.trans_cost[(int64_t)i * N + e] = tc;
+    gst(&a.IO.trans_price[(int64_t)i * N + e], tp);
+    gst(&a.IO.trans_units[(int64_t)i * N + e], tu);
+    gst(&a.IO.trans_cost[(int64_t)i * N + e], tc);
     a.IO.risk[(int64_t)i * N + e] = (uint8_t)risk;
   }
   // exact folds of the final ledger, old prices (Portfolio.cpp:180-197,207-209)
@@ -348,24 +368,6 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
   else { A.pav = A.pav + cur * price; A.pml = A.pml + t_ml; A.pbm = A.pbm + bm; A.pse = A.pse + t_se; }
   A.gsum += fabs(t_ml) + fabs(bm);
 }
-
-// Asynchronous global -> shared copies (LDGSTS): the next pairs' state is prefetched without holding registers.
-// (At the 128-register budget the compiler spilled register prefetches to local memory right after the load --
-// a store that waits for the load -- which made the prefetch a stall; profiles/r1_notes.md.)
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int NKEEP> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory");
-}
-// prefetch rows of one pair: price, ledger, mean_entry, borrowed, units (x2 each), shared mean
-constexpr int kPfRows = 11;
-constexpr int kPfStages = 2;
-// dynamic shared memory of the all-pairs kernel, in rows of BS doubles:
-//   [0, 2 nA) stash | [2 nA, 2 nA + 22) prefetch stages      (54 rows at nA 16: four blocks per SM fit in 228 KB)
-static inline size_t pairs_smem_bytes(int na, int bs) { return sizeof(double) * (size_t)(2 * na + kPfRows * kPfStages) * bs; }
 
 // Shared-memory stash of the all-OU-pairs kernel, one column per thread, four rows per pair p:
 //   before the pair is processed: rows 4p..4p+2 hold its three normals (noise slots 3p..3p+2);
@@ -383,8 +385,8 @@ template <bool PAIRS, int BS>
 __device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t N, int64_t e, int na, int i,
                                           double cur, double newp, double prev_val, double tp, double tu,
                                           double tc, double* st) {
-  a.S.price[(int64_t)i * N + e] = newp;
-  a.IO.obs_price[((int64_t)a.L.head * na + i) * N + e] = newp;  // State.price row (Env.h:202,228,254)
+  gst(&a.S.price[(int64_t)i * N + e], newp);
+  gst(&a.IO.obs_price[((int64_t)a.L.head * na + i) * N + e], newp);  // State.price row (Env.h:202,228,254)
   const double cur_val = cur * newp;
   A.nav = (i == 0) ? cur_val : A.nav + cur_val;
   A.gsum += fabs(cur_val);
@@ -423,17 +425,15 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
   const int na = P.n_assets;
   const int tid = threadIdx.x;
   const int64_t e = (int64_t)blockIdx.x * BS + tid;
-  if (e >= N) return;
   const int mode = a.L.mode;
-  const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
   double* st = stash + tid;  // this thread's column, [row * BS]
+  // the caller's units matrix is (N, nA) env-major: a thread's row is one 128-byte line.  Read as 16-byte
+  // vectors (one per pair) that bypass L1, so that the 64 KB of unit lines per SM do not evict the prefetched state
+  const bool units_v2 = MDG_UNITS_CG && PAIRS && mode == MDG_MODE_MULTI && a.units_v2;
+  if (e >= N) return;
+  const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
   const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;
   const bool moments = shaping && (a.R.shaper == MDG_SHAPER_DSR || a.R.shaper == MDG_SHAPER_DDR);
-  double* pf = st + (int64_t)2 * na * BS;                     // prefetch stages (all-pairs kernel only)
-  const double* pre_ab = nullptr;
-#ifndef MDG_PF
-#define MDG_PF 1
-#endif
   auto prefetch_hint = [&](int pp) {
     const int64_t o0 = (int64_t)(2 * pp) * N + e, o1 = o0 + N;
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.price + o0));
@@ -446,33 +446,18 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.borrowed + o1));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e));
   };
-  auto prefetch_pair = [&](int pp) {
-    double* d = pf + (int64_t)(pp & 1) * (kPfRows * BS);
-    const int64_t o0 = (int64_t)(2 * pp) * N + e, o1 = o0 + N;
-    cp_async8(d + 0 * BS, S.price + o0);      cp_async8(d + 1 * BS, S.price + o1);
-    cp_async8(d + 2 * BS, S.ledger + o0);     cp_async8(d + 3 * BS, S.ledger + o1);
-    cp_async8(d + 4 * BS, S.mean_entry + o0); cp_async8(d + 5 * BS, S.mean_entry + o1);
-    cp_async8(d + 6 * BS, S.borrowed + o0);   cp_async8(d + 7 * BS, S.borrowed + o1);
-    if (mode == MDG_MODE_MULTI) { cp_async8(d + 8 * BS, urow + 2 * pp); cp_async8(d + 9 * BS, urow + 2 * pp + 1); }
-    cp_async8(d + 10 * BS, S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e);
-  };
-  if (PAIRS && MDG_PF == 1) {
+  if (PAIRS) {
+    // The next pair's lines are pulled into L1 with prefetch hints and loaded when needed.  (Holding the next
+    // pair in registers instead made the compiler spill it at the 128-register budget -- a local store right
+    // behind the load, i.e. a full-latency stall; cp.async stages in shared memory were slower too:
+    // profiles/r1_notes.md.)
     prefetch_hint(0);
+    if (MDG_PFDIST > 1 && na > 2) prefetch_hint(1);
     if (mode == MDG_MODE_MULTI) asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
-    if (moments) {
+    if (moments) {  // read at the very end of the kernel: have the lines in L2 by then
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_A + e));
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_B + e));
     }
-  }
-  if (PAIRS && MDG_PF == 0) {  // pairs 0 and 1 (and the shaper moments) start loading before anything else
-    prefetch_pair(0);
-    if (moments) {  // read at the very end of the kernel: pull the lines into L2 now
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_A + e));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_B + e));
-    }
-    cp_async_commit();
-    if (na > 2) prefetch_pair(1);
-    cp_async_commit();
   }
 
   StepAcc A;
@@ -509,7 +494,7 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
     // the kernel is latency-bound at one thread per env) while the first loads are in flight.
     if (!a.IO.normals) {
       const int nslots = 3 * np, nblk = (nslots + 1) >> 1;
-#pragma unroll 4
+#pragma unroll kRngUnroll
       for (int b = 0; b < nblk; ++b) {
         double za, zb;
         normal_block(gid, (uint32_t)b, t_lo, t_hi, k0, k1, za, zb);
@@ -523,27 +508,20 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
       int risk[2];
       // the pair's state arrived through the prefetch stage p & 1 (group p; at most group p+1 is still in flight)
       double mean;
-      if (MDG_PF == 0) {
-        cp_async_wait<1>();
-        const double* d = pf + (int64_t)(p & 1) * (kPfRows * BS);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          price[q] = d[(0 + q) * BS]; cur[q] = d[(2 + q) * BS]; mep[q] = d[(4 + q) * BS]; bm[q] = d[(6 + q) * BS];
-          units[q] = (mode == MDG_MODE_MULTI) ? d[(8 + q) * BS] : 0.;
-        }
-        mean = d[10 * BS];
-      } else {
-        // plain loads of the current pair: their lines were pulled into L1 one iteration ago (no registers held
-        // across the iteration, so nothing to spill), then the hints for the next pair
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int64_t o = (int64_t)(2 * p + q) * N + e;
-          price[q] = S.price[o]; cur[q] = S.ledger[o]; mep[q] = S.mean_entry[o]; bm[q] = S.borrowed[o];
-          units[q] = (mode == MDG_MODE_MULTI) ? urow[2 * p + q] : 0.;
-        }
-        mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
-        if (p + 1 < np) prefetch_hint(p + 1);
+      for (int q = 0; q < 2; ++q) {
+        const int64_t o = (int64_t)(2 * p + q) * N + e;
+        price[q] = S.price[o]; cur[q] = S.ledger[o]; mep[q] = S.mean_entry[o]; bm[q] = S.borrowed[o];
       }
+      if (units_v2) {
+        const double2 u2 = __ldcg(reinterpret_cast<const double2*>(urow + 2 * p));
+        units[0] = u2.x; units[1] = u2.y;
+      } else {
+        units[0] = (mode == MDG_MODE_MULTI) ? urow[2 * p] : 0.;
+        units[1] = (mode == MDG_MODE_MULTI) ? urow[2 * p + 1] : 0.;
+      }
+      mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
+      if (p + MDG_PFDIST < np) prefetch_hint(p + MDG_PFDIST);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int i = 2 * p + q;
@@ -565,13 +543,7 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
         z1 = st[(4 * p + 2) * BS];
       }
       mean += mean * (z_rw * g0.p[2]);
-      S.gstate[(int64_t)g0.gslot * N + e] = mean;
-      // every value of stage p & 1 has been consumed: refill it with pair p + 2 (one group per iteration, possibly
-      // empty, so that wait_group 1 above always means "this pair has landed")
-      if (MDG_PF == 0) {
-        if (p + 2 < np) prefetch_pair(p + 2);
-        cp_async_commit();
-      }
+      gst(&S.gstate[(int64_t)g0.gslot * N + e], mean);
       const double newp0 = price[0] + ((g0.p[0] * (mean - price[0])) + mean * (z0 * g0.p[1]));
       const double newp1 = price[1] + ((g1.p[0] * (mean - price[1])) + mean * (z1 * g1.p[1]));
       post_tick<true, BS>(a, A, N, e, na, 2 * p, cur[0], newp0, prev_val[0], tp[0], tu[0], tc[0], st);
@@ -623,19 +595,19 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
   const int head = a.L.head;
   // BrokerResponse.marginCall (Broker.cpp:135,156): Portfolio::checkRisk() after the last transaction
   if (mode != MDG_MODE_HOLD) a.IO.margin_call[e] = margin_call(cash, A.pav, pml, pbm, pse, maintM) ? 1 : 0;
-  S.cash[e] = cash;
-  S.timestamp[e] = ts + 1;
-  S.folds[(int64_t)MDG_FOLD_AV * N + e] = nav;
-  S.folds[(int64_t)MDG_FOLD_ML * N + e] = pml;
-  S.folds[(int64_t)MDG_FOLD_BM * N + e] = pbm;
-  S.folds[(int64_t)MDG_FOLD_SE * N + e] = pse;
-  S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(cash) + A.gsum;
+  gst(&S.cash[e], cash);
+  gst(&S.timestamp[e], ts + 1);
+  gst(&S.folds[(int64_t)MDG_FOLD_AV * N + e], nav);
+  gst(&S.folds[(int64_t)MDG_FOLD_ML * N + e], pml);
+  gst(&S.folds[(int64_t)MDG_FOLD_BM * N + e], pbm);
+  gst(&S.folds[(int64_t)MDG_FOLD_SE * N + e], pse);
+  gst(&S.folds[(int64_t)MDG_FOLD_G * N + e], fabs(cash) + A.gsum);
   const bool bad_risk = A.bad_risk;
 
   // ---- equity, reward, done (Env.h:192-198, 211-223, 237-249)
   const double currentEq = cash + nav - pbm;
   const double clampv = (mode == MDG_MODE_SINGLE) ? 0.01 : 0.3;
-  a.IO.reward[e] = fast_log(dmax(currentEq / prevEq, clampv));
+  gst(&a.IO.reward[e], fast_log(dmax(currentEq / prevEq, clampv)));
   const bool mc = margin_call(cash, nav, pml, pbm, pse, maintM);
   bool done = mc || (currentEq < 0.1 * P.init_cash);
   if (mode != MDG_MODE_HOLD) done = done || bad_risk;
@@ -648,7 +620,7 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
   double cosv_pp = 0., cosv_qq = 0., cosv_pq = 0.;
   {
     const double w0 = (cash - pbm) * inv_eq;
-    a.IO.obs_port[((int64_t)head * (na + 1)) * N + e] = w0;
+    gst(&a.IO.obs_port[((int64_t)head * (na + 1)) * N + e], w0);
     if (cosine) {
       const double d0 = a.R.desired_portfolio[0];
       cosv_pp = w0 * w0; cosv_qq = d0 * d0; cosv_pq = w0 * d0;
@@ -659,11 +631,11 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
   const int len_before = (shaping && a.R.nstep > 1) ? S.nstep_len[e] : 0;
   int len_after = 0, n_popped = 0;
   double rsum = 0.;
-#pragma unroll 2
+#pragma unroll kTailUnroll
   for (int j = 0; j < na; ++j) {
     const double cur_val = st[stash_cur_row<PAIRS>(j, na) * BS];
     const double w = cur_val * inv_eq;
-    a.IO.obs_port[((int64_t)head * (na + 1) + j + 1) * N + e] = w;
+    gst(&a.IO.obs_port[((int64_t)head * (na + 1) + j + 1) * N + e], w);
     if (cosine) {
       const double dj = a.R.desired_portfolio[j + 1];
       cosv_pp = cosv_pp + w * w; cosv_qq = cosv_qq + dj * dj; cosv_pq = cosv_pq + w * dj;
@@ -675,8 +647,8 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
       if (a.R.reduce_rewards) {
         rsum = (j == 0) ? r : rsum + r;
       } else {
-        a.IO.agent_reward[(int64_t)j * N + e] = r;
-        shaper_add(a, e, j, ra, r, done, len_before, len_after, n_popped, PAIRS ? pre_ab : nullptr, BS);
+        gst(&a.IO.agent_reward[(int64_t)j * N + e], r);
+        shaper_add(a, e, j, ra, r, done, len_before, len_after, n_popped);
       }
     }
   }
@@ -690,17 +662,17 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
       if (a.R.reduce_rewards) {
         rsum = (j == 0) ? r : rsum + r;
       } else {
-        a.IO.agent_reward[(int64_t)j * N + e] = r;
-        shaper_add(a, e, j, ra, r + extra, done, len_before, len_after, n_popped, PAIRS ? pre_ab : nullptr, BS);
+        gst(&a.IO.agent_reward[(int64_t)j * N + e], r);
+        shaper_add(a, e, j, ra, r + extra, done, len_before, len_after, n_popped);
       }
     }
     if (a.R.reduce_rewards) {
-      a.IO.agent_reward[e] = rsum;
-      shaper_add(a, e, 0, 1, rsum + extra, done, len_before, len_after, n_popped, PAIRS ? pre_ab : nullptr, BS);
+      gst(&a.IO.agent_reward[e], rsum);
+      shaper_add(a, e, 0, 1, rsum + extra, done, len_before, len_after, n_popped);
     }
   } else if (shaping && a.R.reduce_rewards) {
-    a.IO.agent_reward[e] = rsum;
-    shaper_add(a, e, 0, 1, rsum, done, len_before, len_after, n_popped, PAIRS ? pre_ab : nullptr, BS);
+    gst(&a.IO.agent_reward[e], rsum);
+    shaper_add(a, e, 0, 1, rsum, done, len_before, len_after, n_popped);
   }
   if (shaping) {
     if (a.R.nstep > 1) S.nstep_len[e] = len_after;
@@ -721,23 +693,13 @@ static inline bool all_ou_pairs(const MdgParams& P) {
   return P.n_normals == 3 * (P.n_assets / 2);
 }
 
-static inline int launch_step(const StepArgs& a) {
+static inline int launch_step(StepArgs& a) {
   const int64_t N = a.L.n_envs;
   cudaStream_t st = (cudaStream_t)a.L.stream;
   const bool pairs = all_ou_pairs(a.P);
   const unsigned grid = (unsigned)((N + 127) / 128);
-  const size_t smem = (pairs && MDG_PF == 0) ? pairs_smem_bytes(a.P.n_assets, 128) : sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
-  static const bool attr_set = [] {  // the all-pairs kernel uses up to 58 KB per block: four blocks fill the SM's 228 KB
-    const int maxb = (int)pairs_smem_bytes(MDG_MAX_ASSETS, 128);
-    cudaFuncSetAttribute(step_kernel<true, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(step_kernel<true, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    if (MDG_PF == 0) {
-      cudaFuncSetAttribute(step_kernel<true, 128, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cudaFuncSetAttribute(step_kernel<true, 128, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    }
-    return true;
-  }();
-  (void)attr_set;
+  a.units_v2 = (a.IO.units && (reinterpret_cast<uintptr_t>(a.IO.units) & 15) == 0 && a.P.n_assets % 2 == 0) ? 1 : 0;
+  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
   if (N <= 148 * 512 * 2) {  // up to two waves at 4 blocks per SM
     if (pairs) step_kernel<true, 128, 4><<<grid, 128, smem, st>>>(a);
     else step_kernel<false, 128, 4><<<grid, 128, smem, st>>>(a);
