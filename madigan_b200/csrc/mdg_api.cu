@@ -187,14 +187,8 @@ __global__ void __launch_bounds__(256) reset_scan_kernel(const __grid_constant__
   a.S.timestamp[e] = ts + fill;  // the later kernels recover ts as timestamp - fill
   a.S.reset_ts[e] = ts + fill;
   a.IO.obs_port[((int64_t)a.L.head * (na + 1)) * N + e] = (cash - 0.) / eq;  // newest row = current state
-  for (int i = 0; i < na; ++i) {  // dataSource_->reset(); fresh Broker/Account/Portfolio (Env.h:150-165)
-    const MdgAssetGen& g = P.gen[i];
-    double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-    a.S.price[(int64_t)i * N + e] = gen_reset(g, a.S.price[(int64_t)i * N + e], gs, N);
-    a.S.ledger[(int64_t)i * N + e] = 0.;
-    a.S.mean_entry[(int64_t)i * N + e] = 0.;
-    a.S.borrowed[(int64_t)i * N + e] = 0.;
-  }
+  // the per-asset part (DataSource::reset(), zeroed ledger rows) is done by reset_recur_kernel, which has one
+  // thread per (env, generator group) instead of one serial 16-asset loop of dependent loads per flagged env
 }
 
 __global__ void __launch_bounds__(256) reset_rng_kernel(const __grid_constant__ ResetWsArgs a) {
@@ -234,7 +228,7 @@ __global__ void __launch_bounds__(256) reset_rng_kernel(const __grid_constant__ 
       philox4x32_10(gid, b, (uint32_t)tick, (uint32_t)(tick >> 32), k0, k1, x0, x1);
       const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
       const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
-      const double r2 = sqrt(-2.0 * fast_log_pos(u1));
+      const double r2 = fast_sqrt_pos(-2.0 * fast_log_pos(u1));
       double sn, cs;
       fast_sincos_2pi(u2, sn, cs);
       double* z = zenv + t * (uint32_t)nn + 2 * b;
@@ -287,6 +281,12 @@ __global__ void __launch_bounds__(128) reset_recur_kernel(const __grid_constant_
                        : P.gen[i0].type == MDG_GEN_SIMPLETREND ? 2 : 1);
     for (int r = 0; r < ngs; ++r) gsl[r] = a.S.gstate[(int64_t)(gslot0 + r) * N + e];
     for (int c = 0; c < cnt; ++c) pr[c] = a.S.price[(int64_t)(i0 + c) * N + e];
+    for (int c = 0; c < cnt; ++c) {  // dataSource_->reset(); fresh Broker/Account/Portfolio (Env.h:150-165)
+      pr[c] = gen_reset(P.gen[i0 + c], pr[c], gsl, 1);
+      a.S.ledger[(int64_t)(i0 + c) * N + e] = 0.;
+      a.S.mean_entry[(int64_t)(i0 + c) * N + e] = 0.;
+      a.S.borrowed[(int64_t)(i0 + c) * N + e] = 0.;
+    }
     const long long ts0 = a.S.timestamp[e] - fill;
     const double* zrow = a.scratch + (int64_t)d * fill * nn;
     double* prow = a.IO.pre_price + ((int64_t)e * k + (k - fill)) * na + i0;

@@ -92,7 +92,7 @@ __device__ __forceinline__ void fill_normals(double* zcol, int zstride, int n_no
     philox4x32_10(c.gid, (uint32_t)b, c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
     const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;  // (0,1)
     const double u2 = (double)(x1 >> 11) * 0x1.0p-53;          // [0,1)
-    const double r = sqrt(-2.0 * fast_log_pos(u1));
+    const double r = fast_sqrt_pos(-2.0 * fast_log_pos(u1));
     double sn, cs;
     fast_sincos_2pi(u2, sn, cs);
     zcol[(2 * b) * zstride] = r * cs;
@@ -127,7 +127,7 @@ static __device__ __noinline__ double draw_normal(LazyDraws& c, int slot) {
     philox4x32_10(c.gid, (uint32_t)blk, c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
     const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
     const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
-    const double r = sqrt(-2.0 * fast_log_pos(u1));
+    const double r = fast_sqrt_pos(-2.0 * fast_log_pos(u1));
     double sn, cs;
     fast_sincos_2pi(u2, sn, cs);
     c.z0 = r * cs;
