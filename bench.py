@@ -200,6 +200,17 @@ def port_rate(sample_envs=8192, sample_steps=24, threads=None):
                       f"64-tick history fill, agent reward + DSR), oracle/mdg_oracle.c with OpenMP over envs, {dt:.2f} s"}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE step-kernel launch of this workload, from the committed
+    `ncu --set full` capture (profiles/step_kernel_traffic.json names the report it was read from); bytes."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "step_kernel_traffic.json")) as f:
+            d = json.load(f)
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def config_dict(n_gpus, slabs):
     return {"workload": "C5 shape: 65,536 envs/GPU x 16-asset portfolios (8 OU pairs), cost .02 + slippage .001, "
                         "DSR reward n=1, 64-step observation ring, auto-reset on done",
@@ -348,7 +359,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(world, slabs),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which, "kernel": "mdg::step_kernel<16,true>",
+                         "traffic": ncu_traffic(), "peak_source": which,
+                         "kernel": "mdg::step_kernel<PAIRS=true, 128 threads, 4 blocks/SM>",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": B * ENVS_PER_GPU},
             "e2e": {"value": world * ENVS_PER_GPU * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -10,6 +10,8 @@ This pins what the reference's own tests leave unpinned: OU / OUPair / noisy Syn
 reward clamp and done logic, slippage and transaction-cost arithmetic, the risk gates under leverage.
 
 Skipped when the reference build is absent (it can only be produced where /root/reference exists)."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -93,7 +95,7 @@ def gen_units(rng, o, n, scale):
     ((.05, 1.), (.001, 0., 0., 0.), 900_000.),
 ])
 def test_env_step_bit_exact_vs_reference(case, margins, costs, scale):
-    rng = np.random.default_rng(hash((case, margins[0])) % 2 ** 31)
+    rng = np.random.default_rng(zlib.crc32(f"{case}/{margins}".encode()))  # stable across processes (hash() is salted)
     r, o, n = build(case, margins, costs, seed=4242)
     z = r.next_normals()
     rs, os_ = r.reset(), o.reset(normals=z)
