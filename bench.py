@@ -333,6 +333,37 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+
+    # ---- timed region 3 (extra key "e2e_actions"): the same end-to-end loop through Env.step_actions -- the agent's
+    # DISCRETE actions (1 byte per asset) cross PCIe and DQN.action_to_transaction (dqn.py:160-179) runs fused in
+    # front of the step, instead of a host-made fp64 units matrix (8 bytes per asset)
+    g = torch.Generator().manual_seed(4242 + rank)
+    host_a8 = [torch.randint(0, 3, (ENVS_PER_GPU, N_ASSETS), generator=g, dtype=torch.int8).pin_memory()
+               for _ in range(4)]
+
+    def e2e_actions_step(i):
+        env = envs[i % slabs]
+        j = i % n_str
+        with torch.cuda.stream(streams[j]):
+            _s, r, d, _ = env.step_actions(host_a8[i % 4], action_atoms=3, unit_size=.05, auto_reset=True)
+            host_reward[j].copy_(env.shaped_reward[0, :, 0], non_blocking=True)
+            host_done[j].copy_(d, non_blocking=True)
+
+    ev_w.record(stream)
+    fork(ev_w)
+    for i in range(max(3, W // 2)):
+        e2e_actions_step(i)
+    join()
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    fork(a0)
+    for i in range(K):
+        e2e_actions_step(i)
+    join()
+    a1.record(stream)
+    barrier()
+    e2e_act_ms = a0.elapsed_time(a1)
     h2d = ENVS_PER_GPU * N_ASSETS * 8
     d2h = ENVS_PER_GPU * 8 + ENVS_PER_GPU
 
@@ -344,10 +375,10 @@ def run_ours(args):
         stats[3] = torch.minimum(stats[3], s2[3]); stats[4] = torch.maximum(stats[4], s2[4])
     stats = parallel.reduce_episode_stats(stats, N_ASSETS)
 
-    t = torch.tensor([ms_total, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, kern_ms, e2e_act_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kern_ms = (float(x) for x in t.cpu())
+    ms_total, e2e_ms, kern_ms, e2e_act_ms = (float(x) for x in t.cpu())
     if rank == 0:
         peak, which = peaks()
         B = bytes_per_env_step()
@@ -364,6 +395,10 @@ def run_ours(args):
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": B * ENVS_PER_GPU},
             "e2e": {"value": world * ENVS_PER_GPU * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_actions": {"value": world * ENVS_PER_GPU * K / (e2e_act_ms * 1e-3), "unit": "env-steps/s",
+                            "h2d_bytes_per_step": ENVS_PER_GPU * N_ASSETS, "d2h_bytes_per_step": d2h,
+                            "api": "Env.step_actions(int8 actions, action_atoms=3, unit_size=.05): "
+                                   "DQN.action_to_transaction fused in front of the step"},
             "gpu_launches": launches, "host_issue_ms_per_step": t_issue, "clocks": clocks,
             "episode_stats": parallel.summarize_stats(stats, N_ASSETS),
         }

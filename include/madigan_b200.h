@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 6
+#define MDG_ABI_VERSION 7
 #define MDG_MAX_ASSETS 16
 #define MDG_GEN_NPARAM 10
 #define MDG_MAX_NSTEP 64
@@ -172,6 +172,12 @@ typedef struct MdgStepIO {
   double *agent_reward;   /* [ra][N] offpolicy_q.py:153-164 (nullable when shaper off) */
   double *shaped_reward;  /* [nstep][ra][N] rewards popped from the n-step buffer this step (row j = j-th pop) */
   int32_t *n_popped;      /* [N] how many rows of shaped_reward are valid this step      */
+  const int8_t *actions;  /* nullable, MDG_MODE_MULTI only: (N,nA) row-major discrete actions in [0, action_atoms).
+                             When given, `units` is ignored and the transaction units are derived in the kernel as
+                             DQN.action_to_transaction does (modelling/algorithm/dqn.py:160-179), from the portfolio
+                             as it stands before the first transaction:
+                               units_i = (a_i - action_atoms/2) * ((unit_size * availableMargin) / price_i),
+                               a_i == 0 closes the position (units_i = -ledger_i, or 0 when flat). */
 } MdgStepIO;
 
 #define MDG_MODE_HOLD 0   /* Env::step()            Env.h:189-204 */
@@ -187,8 +193,9 @@ typedef struct MdgLaunch {
   int32_t mode;        /* MDG_MODE_*                                          */
   int32_t asset_idx;   /* MDG_MODE_SINGLE only                                */
   int32_t nstep_pos;   /* physical n-step ring slot of the entry added now    */
-  int32_t _pad;
+  int32_t action_atoms; /* MdgStepIO.actions only: number of discrete actions per asset (dqn.py:166) */
   void *stream;        /* cudaStream_t                                        */
+  double unit_size;    /* MdgStepIO.actions only: fraction of availableMargin per action unit (dqn.py:164) */
 } MdgLaunch;
 
 /* derived accounting, Portfolio.cpp:140-235,243-252; any pointer may be NULL */

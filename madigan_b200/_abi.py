@@ -5,7 +5,7 @@ checks the struct sizes against the compiled library (``mdg_sizeof``).
 """
 import ctypes as C
 
-MDG_ABI_VERSION = 6
+MDG_ABI_VERSION = 7
 MDG_MAX_ASSETS = 16
 MDG_GEN_NPARAM = 10
 MDG_MAX_NSTEP = 64
@@ -65,14 +65,14 @@ class MdgStepIO(C.Structure):
     _fields_ = [(n, _dp) for n in ("units", "normals", "uniforms", "obs_price", "obs_port",
                                    "pre_price", "reward", "done", "trans_price", "trans_units",
                                    "trans_cost", "risk", "margin_call", "agent_reward",
-                                   "shaped_reward", "n_popped")]
+                                   "shaped_reward", "n_popped", "actions")]
 
 
 class MdgLaunch(C.Structure):
     _fields_ = [("n_envs", C.c_int64), ("env_offset", C.c_int64), ("seed", C.c_uint64),
                 ("window", C.c_int32), ("head", C.c_int32), ("mode", C.c_int32),
-                ("asset_idx", C.c_int32), ("nstep_pos", C.c_int32), ("_pad", C.c_int32),
-                ("stream", C.c_void_p)]
+                ("asset_idx", C.c_int32), ("nstep_pos", C.c_int32), ("action_atoms", C.c_int32),
+                ("stream", C.c_void_p), ("unit_size", C.c_double)]
 
 
 class MdgWindow(C.Structure):

@@ -436,7 +436,10 @@ extern "C" int mdg_step(const MdgParams* P, const MdgReward* R, const MdgState* 
   if (!S->folds) return set_err(MDG_E_INVALID, "state.folds is null");
   if (L->window < 1 || L->head < 0 || L->head >= L->window) return set_err(MDG_E_INVALID, "bad window/head");
   if (L->mode < MDG_MODE_HOLD || L->mode > MDG_MODE_SINGLE) return set_err(MDG_E_INVALID, "bad mode");
-  if (L->mode != MDG_MODE_HOLD && !IO->units) return set_err(MDG_E_INVALID, "units is null");
+  const bool by_actions = L->mode == MDG_MODE_MULTI && IO->actions;
+  if (L->mode != MDG_MODE_HOLD && !IO->units && !by_actions) return set_err(MDG_E_INVALID, "units is null");
+  if (by_actions && (L->action_atoms < 1 || L->action_atoms > 127))
+    return set_err(MDG_E_INVALID, "action_atoms must be in [1, 127] with io.actions");
   if (L->mode == MDG_MODE_SINGLE && (L->asset_idx < 0 || L->asset_idx >= P->n_assets))
     return set_err(MDG_E_INVALID, "asset index out of range");  // std::out_of_range -> IndexError
   if (L->n_envs == 0) return MDG_OK;

@@ -382,6 +382,12 @@ template <bool PAIRS> __device__ __forceinline__ int stash_pm_row(int j, int na)
   return PAIRS ? 4 * (j >> 1) + 2 + (j & 1) : na + j;
 }
 
+// dqn.py:165-178: centred action times (unit_size * availableMargin / price); action 0 closes an open position
+__device__ __forceinline__ double action_units(int act, int half, double scale, double price, double cur) {
+  if (act == 0) return (cur != 0.) ? -cur : 0.;
+  return (double)(act - half) * (scale / price);
+}
+
 // after the tick of asset i: state/observation stores, fold of the new position value, reward stash
 template <bool PAIRS, int BS>
 __device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t N, int64_t e, int na, int i,
@@ -416,7 +422,7 @@ __device__ __forceinline__ void normal_block(uint32_t gid, uint32_t blk, uint32_
 //     wave (that launch is latency-bound: a second wave would cost as much as the first);
 //   168 registers -> 3 blocks per SM, no spills: best throughput when there are many waves (>= 262,144 envs).
 // (64-thread blocks x 7 per SM at 144 registers were measured slower than either.)
-template <bool PAIRS, int BS, int MINB>
+template <bool PAIRS, int BS, int MINB, bool ACTIONS>
 __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ StepArgs a) {
   // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff (and, in the
   // all-pairs kernel, this step's normals before they are consumed; see stash_normal_row)
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
   const bool units_v2 = MDG_UNITS_CG && PAIRS && mode == MDG_MODE_MULTI && a.units_v2;
   if (e >= N) return;
   const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
-  const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;
+  const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;  // unused with actions
   const bool moments = shaping && (a.R.shaper == MDG_SHAPER_DSR || a.R.shaper == MDG_SHAPER_DDR);
   auto prefetch_hint = [&](int pp) {
     const int64_t o0 = (int64_t)(2 * pp) * N + e, o1 = o0 + N;
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
     // profiles/r1_notes.md.)
     prefetch_hint(0);
     if (MDG_PFDIST > 1 && na > 2) prefetch_hint(1);
-    if (mode == MDG_MODE_MULTI) asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
+    if (mode == MDG_MODE_MULTI && urow) asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
     if (moments) {  // read at the very end of the kernel: have the lines in L2 by then
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_A + e));
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a.S.shaper_B + e));
@@ -476,6 +482,12 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
   A.pav = A.pml = A.pbm = A.pse = A.nav = A.gsum = 0.;
   A.bad_risk = false;
   const double prevEq = A.cash + A.rAV - A.rBM;  // Env.h:190,208,234
+  // DQN.action_to_transaction (dqn.py:160-179) fused in front of the step: units from discrete actions and the
+  // availableMargin of the incoming portfolio (Portfolio.cpp:229-231), one scale for every asset
+  // (a template parameter: the three extra live values cost 3 % in the units kernel at its 128-register budget)
+  const int8_t* arow = (ACTIONS && mode == MDG_MODE_MULTI && a.IO.actions) ? a.IO.actions + e * na : nullptr;
+  const double act_scale = arow ? a.L.unit_size * (((A.cash + A.rSE) + (A.rAV - A.rML)) / P.required_margin) : 0.;
+  const int act_half = a.L.action_atoms / 2;
 
   StepConsts c;
   c.reqM = P.required_margin;
@@ -519,8 +531,12 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
         const double2 u2 = __ldcg(reinterpret_cast<const double2*>(urow + 2 * p));
         units[0] = u2.x; units[1] = u2.y;
       } else {
-        units[0] = (mode == MDG_MODE_MULTI) ? urow[2 * p] : 0.;
-        units[1] = (mode == MDG_MODE_MULTI) ? urow[2 * p + 1] : 0.;
+        units[0] = (mode == MDG_MODE_MULTI && !arow) ? urow[2 * p] : 0.;
+        units[1] = (mode == MDG_MODE_MULTI && !arow) ? urow[2 * p + 1] : 0.;
+      }
+      if (arow) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) units[q] = action_units(arow[2 * p + q], act_half, act_scale, price[q], cur[q]);
       }
       mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
       if (p + MDG_PFDIST < np) prefetch_hint(p + MDG_PFDIST);
@@ -566,7 +582,8 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
       double mep = S.mean_entry[(int64_t)i * N + e];
       double bm = S.borrowed[(int64_t)i * N + e];
       double units = 0.;
-      if (mode == MDG_MODE_MULTI) units = urow[i];
+      if (arow) units = action_units(arow[i], act_half, act_scale, price, cur);
+      else if (mode == MDG_MODE_MULTI) units = urow[i];
       else if (mode == MDG_MODE_SINGLE && i == a.L.asset_idx) units = urow[0];
       double tp, tu, tc, prev_val;
       int risk;
@@ -702,13 +719,17 @@ static inline int launch_step(StepArgs& a) {
   const unsigned grid = (unsigned)((N + 127) / 128);
   a.units_v2 = (a.IO.units && (reinterpret_cast<uintptr_t>(a.IO.units) & 15) == 0 && a.P.n_assets % 2 == 0) ? 1 : 0;
   const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
-  if (N <= 148 * 512 * 2) {  // up to two waves at 4 blocks per SM
-    if (pairs) step_kernel<true, 128, 4><<<grid, 128, smem, st>>>(a);
-    else step_kernel<false, 128, 4><<<grid, 128, smem, st>>>(a);
+  const bool acts = a.L.mode == MDG_MODE_MULTI && a.IO.actions;
+  const bool small = N <= 148 * 512 * 2;  // up to two waves at 4 blocks per SM
+#define MDG_LAUNCH(PAIRS_, MINB_, ACT_) step_kernel<PAIRS_, 128, MINB_, ACT_><<<grid, 128, smem, st>>>(a)
+  if (small) {
+    if (pairs) { if (acts) MDG_LAUNCH(true, 4, true); else MDG_LAUNCH(true, 4, false); }
+    else { if (acts) MDG_LAUNCH(false, 4, true); else MDG_LAUNCH(false, 4, false); }
   } else {
-    if (pairs) step_kernel<true, 128, 3><<<grid, 128, smem, st>>>(a);
-    else step_kernel<false, 128, 3><<<grid, 128, smem, st>>>(a);
+    if (pairs) { if (acts) MDG_LAUNCH(true, 3, true); else MDG_LAUNCH(true, 3, false); }
+    else { if (acts) MDG_LAUNCH(false, 3, true); else MDG_LAUNCH(false, 3, false); }
   }
+#undef MDG_LAUNCH
   return cuda_err(cudaGetLastError(), "mdg_step launch");
 }
 

@@ -328,6 +328,51 @@ class Env:
         t = self.t
         return self._state(), t["reward"], t["done"], self._info
 
+    def step_actions(self, actions, *, action_atoms, unit_size, normals=None, uniforms=None, auto_reset=False):
+        """``env.step(agent.action_to_transaction(actions))`` in one launch: ``actions`` is an (N, nA) integer tensor
+        of discrete actions in [0, action_atoms); the kernel converts them to transaction units exactly as
+        ``DQN.action_to_transaction`` does (modelling/algorithm/dqn.py:160-179 -- ``(a - atoms//2) * unit_size *
+        availableMargin / price``, action 0 closes an open position) and steps.  The action matrix is 1 byte per
+        asset instead of the 8 of a units matrix.  Returns what ``step(units)`` returns."""
+        io = self._IO
+        with self._device_ctx():
+            a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(actions)
+            if a.dtype != torch.int8:
+                a = a.to(torch.int8)
+            if a.shape != self._want_multi:
+                if self.N == 1 and a.dim() == 1:
+                    a = a.unsqueeze(0)
+                if a.shape != self._want_multi:
+                    raise ValueError(f"actions must have shape {tuple(self._want_multi)}, got {tuple(a.shape)}")
+            if not a.is_cuda or a.device != self.device or not a.is_contiguous():
+                if "actions" not in self.t:
+                    self.t["actions"] = torch.empty((self.N, self.nA), dtype=torch.int8, device=self.device)
+                self.t["actions"].copy_(a, non_blocking=True)
+                a = self.t["actions"]
+            io.units = None
+            io.actions = a.data_ptr()
+            try:
+                if normals is None and uniforms is None:
+                    io.normals = io.uniforms = None
+                    keep = None
+                else:
+                    io.normals, io.uniforms, keep = self._noise(normals, uniforms)
+                self.head = (self.head + 1) % self.k
+                self.n_valid = min(self.k, self.n_valid + 1)
+                L = self._launch(A.MODE_MULTI, 0)
+                L.action_atoms, L.unit_size = int(action_atoms), float(unit_size)
+                check(self._lib.mdg_step(C.byref(self.P), C.byref(self.R), C.byref(self._S), C.byref(io), C.byref(L)))
+            finally:
+                io.actions = None
+            self.launches += 1
+            if self.R.shaper != A.SHAPER_OFF:
+                self._gstep += 1
+            self._version += 1
+            if auto_reset:
+                self._reset_launch(self.t["done"], self.k, True, None, None)
+        t = self.t
+        return self._state(), t["reward"], t["done"], self._info
+
     # ------------------------------------------------------------------ in-kernel rewards
     @property
     def agent_reward(self):

@@ -754,6 +754,18 @@ static void write_row(const MdgStepIO *io, const MdgLaunch *L, int nA, int64_t N
   (void)L;
 }
 
+/* DQN.action_to_transaction, modelling/algorithm/dqn.py:160-179: units from discrete actions */
+void orc_action_units(const OrcEnv *e, const int8_t *actions, int action_atoms, double unit_size, double *units) {
+  const double scale = unit_size * orc_available_margin(e); /* :164 self.unit_size * self._env.availableMargin */
+  const int half = action_atoms / 2;                        /* :166 action_atoms // 2 */
+  for (int j = 0; j < e->P.n_assets; ++j) {
+    const double per = scale / e->price[j];                 /* :164-165 ... / self._env.currentPrices */
+    units[j] = (double)(actions[j] - half) * per;           /* :169 actions_centered * units */
+    if (actions[j] == 0)                                    /* :171-177 action 0 closes an open position */
+      units[j] = (e->ledger[j] != 0.) ? -e->ledger[j] : 0.;
+  }
+}
+
 void orc_batch_step(OrcBatch *b, const MdgStepIO *io, const MdgLaunch *L, int threads) {
   const int64_t N = b->n;
   (void)threads;
@@ -765,7 +777,9 @@ void orc_batch_step(OrcBatch *b, const MdgStepIO *io, const MdgLaunch *L, int th
     const double *pn = 0, *pu = 0;
     if (io->normals) { for (int s = 0; s < e->P.n_normals; ++s) nz[s] = io->normals[s * N + i]; pn = nz; }
     if (io->uniforms) { for (int s = 0; s < e->P.n_uniforms; ++s) uz[s] = io->uniforms[s * N + i]; pu = uz; }
-    if (L->mode == MDG_MODE_MULTI) for (int j = 0; j < nA; ++j) un[j] = io->units[i * nA + j];
+    if (L->mode == MDG_MODE_MULTI && io->actions)
+      orc_action_units(e, io->actions + i * nA, L->action_atoms, L->unit_size, un);
+    else if (L->mode == MDG_MODE_MULTI) for (int j = 0; j < nA; ++j) un[j] = io->units[i * nA + j];
     if (L->mode == MDG_MODE_SINGLE) un[0] = io->units[i];
     OrcStepOut o;
     orc_step(e, L->mode, un, L->asset_idx, pn, pu, &o);

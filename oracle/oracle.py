@@ -88,6 +88,7 @@ def lib():
         L.orc_draw_normal.restype = dbl
         L.orc_draw_uniform.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int]
         L.orc_draw_uniform.restype = dbl
+        L.orc_action_units.argtypes = [pe, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.orc_batch_create.argtypes = [C.c_int64, C.POINTER(A.MdgParams), C.POINTER(A.MdgReward), C.c_uint64, C.c_int64]
         L.orc_batch_create.restype = C.c_void_p
         L.orc_batch_destroy.argtypes = [C.c_void_p]
@@ -177,6 +178,14 @@ class OracleEnv:
         return np.array([list(o.shaped[k][:ra]) for k in range(o.n_popped)]).reshape(o.n_popped, ra), o.n_popped
 
     # -- Portfolio / Broker primitives
+    def action_units(self, actions, action_atoms, unit_size):
+        """DQN.action_to_transaction (dqn.py:160-179) on the current portfolio: discrete actions -> units"""
+        a = np.ascontiguousarray(actions, dtype=np.int8)
+        out = np.zeros(self.nA)
+        self.L.orc_action_units(C.byref(self.e), a.ctypes.data_as(C.c_void_p), int(action_atoms), float(unit_size),
+                                out.ctypes.data_as(C.c_void_p))
+        return out
+
     def handleTransaction(self, i, price, units, cost=0.):
         self.L.orc_handle_transaction(C.byref(self.e), i, price, units, cost)
 
@@ -306,6 +315,18 @@ class OracleBatch:
         mode = A.MODE_HOLD if units is None else (A.MODE_SINGLE if asset_idx is not None else A.MODE_MULTI)
         io = self._io(units, normals, uniforms)
         L = self._launch(mode, 0 if asset_idx is None else int(asset_idx))
+        self.L.orc_batch_step(self.h, C.byref(io), C.byref(L), self.threads)
+
+    def step_actions(self, actions, action_atoms, unit_size, normals=None, uniforms=None):
+        """actions: (N,nA) int8 discrete actions -> units as DQN.action_to_transaction (dqn.py:160-179), then step."""
+        self.head = (self.head + 1) % self.k
+        self.n_valid = min(self.k, self.n_valid + 1)
+        io = self._io(None, normals, uniforms)
+        acts = np.ascontiguousarray(actions, dtype=np.int8)
+        self._keep.append(acts)
+        io.actions = acts.ctypes.data_as(C.c_void_p)
+        L = self._launch(A.MODE_MULTI)
+        L.action_atoms, L.unit_size = int(action_atoms), float(unit_size)
         self.L.orc_batch_step(self.h, C.byref(io), C.byref(L), self.threads)
 
     def state(self):
