@@ -68,11 +68,11 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.samples.append([x.strip() for x in line.split(",")])
+                self.samples.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
         except Exception:
             pass
 
@@ -84,10 +84,15 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """median SM clock / reasons over the samples taken between host times t0 and t1 (the timed region,
+        which ends with a device synchronize); all samples when the window caught none"""
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for s in self.samples:
+        inside = [s[1:] for s in self.samples if t0 is None or (t0 <= s[0] <= t1)]
+        if not inside:
+            inside = [s[1:] for s in self.samples]
+        for s in inside:
             try:
                 sm.append(float(s[1])); mx.append(float(s[2]))
                 for n, v in zip(names, s[4:8]):
@@ -276,6 +281,7 @@ def run_ours(args):
     launches0 = sum(e.launches for e in envs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.perf_counter()
     ev0.record(stream)
     fork(ev0)
     t_issue = time.perf_counter()
@@ -287,8 +293,9 @@ def run_ours(args):
     barrier()
     launches = sum(e.launches for e in envs) - launches0
     ms_total = ev0.elapsed_time(ev1)
+    t_region1 = time.perf_counter()
     sampler.stop()
-    clocks = sampler.summary()
+    clocks = sampler.summary(t_region0, t_region1)
 
     # ---- the dominant kernel alone (roofline): the step kernel of consecutive slabs back to back on ONE stream,
     # CUDA events around every launch, resets outside the event pairs
@@ -459,8 +466,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slabs", type=int, default=8)
     ap.add_argument("--streams", type=int, default=4)
