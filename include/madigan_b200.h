@@ -281,9 +281,15 @@ typedef struct MdgWindow {
   int32_t norm_type;         /* MDG_NORM_*                                                     */
   int32_t flat_prefix;       /* prefix==NULL and rows older than the reset are [1,0,...,0]     */
   int32_t out_dtype, out_layout;
-  void *out;
+  void *out;                 /* (N, n_valid, F_out) or (N, F_out, n_valid)                    */
   void *stream;
+  int32_t transform;         /* MDG_XFORM_*: the other price stackers of utils/preprocessor.py */
+  int32_t _pad;
 } MdgWindow;
+#define MDG_XFORM_NONE 0       /* StackerDiscrete            preprocessor.py:143-199, F_out = F            */
+#define MDG_XFORM_PAIR_RATIO 1 /* StackerDiscretePairs       :295-321  price[:,0]/price[:,1], F = 2 -> F_out = 1, then the normaliser */
+#define MDG_XFORM_RETURNS 2    /* StackerDiscreteReturns     :324-333  normaliser, then np.diff over the LAST axis
+                                  (features, as the reference does): F_out = F - 1 */
 int mdg_materialise_window(const MdgWindow *w);
 /* (N, n_valid) int64 timestamps of the window rows: timestamp[e] - (n_valid-1-s) */
 int mdg_materialise_time(const int64_t *timestamp, int64_t n_envs, int32_t n_valid, int64_t *out, void *stream);

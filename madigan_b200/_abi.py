@@ -6,6 +6,7 @@ checks the struct sizes against the compiled library (``mdg_sizeof``).
 import ctypes as C
 
 MDG_ABI_VERSION = 7
+XFORM_NONE, XFORM_PAIR_RATIO, XFORM_RETURNS = 0, 1, 2
 MDG_MAX_ASSETS = 16
 MDG_GEN_NPARAM = 10
 MDG_MAX_NSTEP = 64
@@ -79,7 +80,7 @@ class MdgWindow(C.Structure):
     _fields_ = [("ring", _dp), ("prefix", _dp), ("timestamp", _dp), ("reset_ts", _dp), ("n_envs", C.c_int64),
                 ("n_feats", C.c_int32), ("window", C.c_int32), ("head", C.c_int32), ("n_valid", C.c_int32),
                 ("norm_type", C.c_int32), ("flat_prefix", C.c_int32), ("out_dtype", C.c_int32),
-                ("out_layout", C.c_int32), ("out", _dp), ("stream", _dp)]
+                ("out_layout", C.c_int32), ("out", _dp), ("stream", _dp), ("transform", C.c_int32), ("_pad", C.c_int32)]
 
 
 class MdgDerived(C.Structure):

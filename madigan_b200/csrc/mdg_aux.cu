@@ -136,6 +136,7 @@ struct WindowArgs {
   void* out;
   int64_t N;
   int F, k, head, n_valid, norm, out_dtype, layout, flat_prefix;
+  int xform, Feff, Fout;  // Feff: features the normaliser sees; Fout: features written
   int envs;     // envs per block (blockDim.x)
   int sstride;  // smem stride between rows s (doubles)
   int estride;  // smem stride between envs   (doubles)
@@ -170,9 +171,15 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
     }
   }
   __syncthreads();
+  const int Fe = a.Feff;
+  if (a.xform == MDG_XFORM_PAIR_RATIO) {  // price[:, 0] / price[:, 1]  (preprocessor.py:314-315)
+    if (live && f == 0)
+      for (int s = 0; s < nv; ++s) col[s * a.sstride] = col[s * a.sstride] / col[s * a.sstride + 1];
+    __syncthreads();
+  }
 
   // phase 2: normalise in place
-  if (live) {
+  if (live && f < Fe) {
     switch (a.norm) {
       case MDG_NORM_LOOKBACK: {  // x / x[-1]
         const double last = col[(nv - 1) * a.sstride];
@@ -191,14 +198,14 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
         }
         break;
       case MDG_NORM_STANDARD: {  // nan_to_num((x - mean(0)) / std(0))
-        const bool pw = (F == 1);
+        const bool pw = (Fe == 1);
         const double mean = col_sum<0>(col, nv, a.sstride, 0., pw) / nv;
         const double sd = sqrt(col_sum<1>(col, nv, a.sstride, mean, pw) / nv);
         for (int s = 0; s < nv; ++s) col[s * a.sstride] = nan_to_num((col[s * a.sstride] - mean) / sd);
         break;
       }
       case MDG_NORM_LOG_STANDARD: {  // x = log(x); nan_to_num((x - nanmean) / nanstd)
-        const bool pw = (F == 1);
+        const bool pw = (Fe == 1);
         int cnt = 0;
         for (int s = 0; s < nv; ++s) {
           const double x = log(col[s * a.sstride]);
@@ -225,7 +232,7 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
       int w = 1;
       double prev = row[0];
       row[0] = prev / acc;
-      for (int i = 1; i < F; ++i) {
+      for (int i = 1; i < Fe; ++i) {
         const double x = row[i];
         if (x == x) { acc = acc + x; w += 1; }
         row[i] = x / (acc / w);
@@ -236,15 +243,17 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
 
   // phase 3: contiguous write-out of the block's windows
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
-  const int per_env = nv * F;
+  const int Fo = a.Fout;
+  const int per_env = nv * Fo;
   const int64_t rows = (a.N - e0) < a.envs ? (a.N - e0) : a.envs;
   const int64_t total = rows * per_env;
   for (int64_t idx = tid; idx < total; idx += nthr) {
     const int re = (int)(idx / per_env);
     const int r = (int)(idx - (int64_t)re * per_env);
     int s, ff;
-    if (a.layout == MDG_LAYOUT_NKF) { s = r / F; ff = r - s * F; } else { ff = r / nv; s = r - ff * nv; }
-    const double v = tile[(int64_t)re * a.estride + (int64_t)s * a.sstride + ff];
+    if (a.layout == MDG_LAYOUT_NKF) { s = r / Fo; ff = r - s * Fo; } else { ff = r / nv; s = r - ff * nv; }
+    const double* tp = tile + (int64_t)re * a.estride + (int64_t)s * a.sstride + ff;
+    const double v = (a.xform == MDG_XFORM_RETURNS) ? tp[1] - tp[0] : tp[0];  // np.diff(price): last axis (:330)
     const int64_t o = e0 * per_env + idx;
     if (a.out_dtype == MDG_DTYPE_F32) ((float*)a.out)[o] = (float)v; else ((double*)a.out)[o] = v;
   }
@@ -382,8 +391,15 @@ extern "C" int mdg_materialise_window(const MdgWindow* w) {
   if (w->out_layout != MDG_LAYOUT_NKF && w->out_layout != MDG_LAYOUT_NFK) return set_err(MDG_E_INVALID, "bad layout");
   if (w->timestamp && !w->reset_ts) return set_err(MDG_E_INVALID, "timestamp given without reset_ts");
   if (w->timestamp && !w->prefix && !w->flat_prefix) return set_err(MDG_E_INVALID, "no prefix source for rows older than the reset");
+  if (w->transform < MDG_XFORM_NONE || w->transform > MDG_XFORM_RETURNS) return set_err(MDG_E_INVALID, "bad transform");
+  if (w->transform == MDG_XFORM_PAIR_RATIO && n_feats != 2)
+    return set_err(MDG_E_INVALID, "the pair-ratio window needs exactly 2 features");  // preprocessor.py:301 assert
   if (w->n_envs <= 0) return w->n_envs == 0 ? MDG_OK : set_err(MDG_E_INVALID, "n_envs < 0");
+  if (w->transform == MDG_XFORM_RETURNS && n_feats == 1) return MDG_OK;  // np.diff of one feature: (k, 0), nothing to write
   WindowArgs a;
+  a.xform = w->transform;
+  a.Feff = (w->transform == MDG_XFORM_PAIR_RATIO) ? 1 : n_feats;
+  a.Fout = (w->transform == MDG_XFORM_PAIR_RATIO) ? 1 : (w->transform == MDG_XFORM_RETURNS ? n_feats - 1 : n_feats);
   a.ring = w->ring; a.prefix = w->prefix; a.timestamp = w->timestamp; a.reset_ts = w->reset_ts;
   a.out = w->out; a.N = w->n_envs; a.F = n_feats; a.k = window; a.head = head; a.n_valid = n_valid;
   a.norm = w->norm_type; a.out_dtype = w->out_dtype; a.layout = w->out_layout; a.flat_prefix = w->flat_prefix;

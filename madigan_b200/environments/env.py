@@ -514,26 +514,30 @@ class Env:
     def broker(self): return _View(self)
 
     # ------------------------------------------------------------------ window / stats / checkpoint
-    def window(self, norm_type=None, dtype=torch.float64, channels_first=False, n_valid=None, out=None):
+    def window(self, norm_type=None, dtype=torch.float64, channels_first=False, n_valid=None, out=None,
+               transform=A.XFORM_NONE):
         """Materialise the price window ``(N, n_valid, nF)`` (or ``(N, nF, n_valid)``) from the observation
-        ring, normalised as ``make_normalizer(norm_type)`` (reference: utils/preprocessor.py:53-107,183-189)."""
+        ring, normalised as ``make_normalizer(norm_type)`` (reference: utils/preprocessor.py:53-107,183-189).
+        ``transform``: ``XFORM_PAIR_RATIO`` (StackerDiscretePairs, nF 2 -> 1) or ``XFORM_RETURNS``
+        (StackerDiscreteReturns, nF -> nF-1)."""
         from ..utils.preprocessor import NORM_TYPES
         nv = self.n_valid if n_valid is None else int(n_valid)
         norm = NORM_TYPES[norm_type]
-        shape = (self.N, self.nA, nv) if channels_first else (self.N, nv, self.nA)
+        f_out = 1 if transform == A.XFORM_PAIR_RATIO else (self.nA - 1 if transform == A.XFORM_RETURNS else self.nA)
+        shape = (self.N, f_out, nv) if channels_first else (self.N, nv, f_out)
         if out is None:
             out = torch.empty(shape, dtype=dtype, device=self.device)
         dt = A.DTYPE_F32 if out.dtype == torch.float32 else A.DTYPE_F64
         self._window_launch(self.t["obs_price"], self.t["pre_price"], 0, self.nA, nv, norm, out, dt,
-                            A.LAYOUT_NFK if channels_first else A.LAYOUT_NKF)
+                            A.LAYOUT_NFK if channels_first else A.LAYOUT_NKF, transform)
         return out
 
-    def _window_launch(self, ring, prefix, flat_prefix, n_feats, nv, norm, out, dt, layout):
+    def _window_launch(self, ring, prefix, flat_prefix, n_feats, nv, norm, out, dt, layout, transform=A.XFORM_NONE):
         w = A.MdgWindow(ring=ring.data_ptr(), prefix=None if prefix is None else prefix.data_ptr(),
                         timestamp=self.t["timestamp"].data_ptr(), reset_ts=self.t["reset_ts"].data_ptr(),
                         n_envs=self.N, n_feats=n_feats, window=self.k, head=self.head, n_valid=nv, norm_type=norm,
                         flat_prefix=flat_prefix, out_dtype=dt, out_layout=layout, out=out.data_ptr(),
-                        stream=torch.cuda.current_stream(self.device).cuda_stream)
+                        stream=torch.cuda.current_stream(self.device).cuda_stream, transform=transform)
         with torch.cuda.device(self.device):
             check(self._lib.mdg_materialise_window(C.byref(w)))
         self.launches += 1

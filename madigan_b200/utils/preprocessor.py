@@ -32,11 +32,16 @@ def make_preprocessor(config, n_feats):
     ptype = config["preprocessor_type"] if isinstance(config, dict) else config.preprocessor_type
     if ptype in ("WindowedStacker", "StackerDiscrete"):
         return StackerDiscrete.from_config(config, n_feats)
+    if ptype == "StackerDiscretePairs":
+        return StackerDiscretePairs.from_config(config, n_feats)
+    if ptype == "StackerDiscreteReturns":
+        return StackerDiscreteReturns.from_config(config, n_feats)
     raise NotImplementedError(f"{ptype} is not implemented ")
 
 
 class StackerDiscrete:
     """reference: utils/preprocessor.py:143-199."""
+    transform = A.XFORM_NONE
 
     def __init__(self, window_len, n_features, norm=True, norm_type="standard_normal", dtype=torch.float64,
                  channels_first=False):
@@ -92,15 +97,18 @@ class StackerDiscrete:
         if env is None or self._len == 0:
             raise RuntimeError("no data streamed yet")
         price = env.window(self.norm_type, dtype=self.dtype, channels_first=self.channels_first,
-                           n_valid=self._len)
-        return State(price, env.portfolio_window(self._len), env.time_window(self._len))
+                           n_valid=self._len, transform=self.transform)
+        port, time = env.portfolio_window(self._len), env.time_window(self._len)
+        if self.transform == A.XFORM_RETURNS:  # preprocessor.py:331-332: portfolio[1:], timestamp[1:]
+            port, time = port[:, 1:], time[:, 1:]
+        return State(price, port, time)
 
     def current_price(self, out=None, dtype=None, channels_first=None):
         """Price window only (what the agents' nets consume), optionally fp32 / channels-first."""
         env = self._env
         return env.window(self.norm_type, dtype=dtype or self.dtype,
                           channels_first=self.channels_first if channels_first is None else channels_first,
-                          n_valid=self._len, out=out)
+                          n_valid=self._len, out=out, transform=self.transform)
 
     def initialize_history(self, env):
         """reference: utils/preprocessor.py:191-194 -- no-action steps until the window is full."""
@@ -116,3 +124,20 @@ class StackerDiscrete:
         """After ``env.reset(fill_history=True)`` (reset + history fill in one launch)."""
         self._bind(env)
         self._len = env.n_valid
+
+
+class StackerDiscretePairs(StackerDiscrete):
+    """reference: utils/preprocessor.py:295-321 -- the window of the ratio price[:, 0] / price[:, 1] of a
+    two-feature source, shape (k, 1), then the normaliser."""
+    transform = A.XFORM_PAIR_RATIO
+
+    def __init__(self, window_len, n_features, norm=True, norm_type="standard_normal", **kw):
+        assert n_features == 2  # preprocessor.py:301
+        super().__init__(window_len, n_features, norm, norm_type, **kw)
+        self._feature_output_shape = (self.k, 1)
+
+
+class StackerDiscreteReturns(StackerDiscrete):
+    """reference: utils/preprocessor.py:324-333 -- normaliser, then ``np.diff(price)``, which runs over the LAST
+    axis (features): price (k, nF-1); portfolio and timestamp lose their first row."""
+    transform = A.XFORM_RETURNS

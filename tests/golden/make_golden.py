@@ -134,8 +134,35 @@ def make_preprocessor(preprocessor, State):
     np.savez_compressed(os.path.join(HERE, "preprocessor.npz"), **data)
 
 
+def make_stackers(preprocessor, State):
+    """StackerDiscretePairs (preprocessor.py:295-321) and StackerDiscreteReturns (:324-333)."""
+    rng = np.random.default_rng(11)
+    k, T = 12, 30
+    data = {}
+    for name, nF in (("pairs", 2), ("returns", 4)):
+        prices = np.abs(10 + np.cumsum(rng.standard_normal((T, nF)) * .3, axis=0)) + .5
+        ports = rng.dirichlet(np.ones(nF + 1), size=T)
+        data[f"{name}_prices"], data[f"{name}_ports"] = prices, ports
+        for norm in NORMS:
+            cls = preprocessor.StackerDiscretePairs if name == "pairs" else preprocessor.StackerDiscreteReturns
+            pre = cls(k, nF, norm=norm is not None, norm_type=norm or "lookback")
+            outs, ports_out, times_out, steps = [], [], [], []
+            for t in range(T):
+                pre.stream_state(State(prices[t], ports[t], np.int64(t + 1)))
+                if t in (11, 12, 20, 29):  # full windows only
+                    cd = pre.current_data()
+                    outs.append(cd.price); ports_out.append(cd.portfolio); times_out.append(cd.timestamp)
+                    steps.append(t)
+            data[f"{name}_out_{norm}"] = np.array(outs)
+            data[f"{name}_port"] = np.array(ports_out)
+            data[f"{name}_time"] = np.array(times_out)
+            data["steps"] = np.array(steps)
+    np.savez_compressed(os.path.join(HERE, "stackers.npz"), **data)
+
+
 if __name__ == "__main__":
     nstep_buffer, preprocessor, SARSD, State = import_reference()
     n = make_shapers(nstep_buffer, SARSD, State)
     make_preprocessor(preprocessor, State)
+    make_stackers(preprocessor, State)
     print("golden vectors written:", n, "shaper arrays + preprocessor windows")

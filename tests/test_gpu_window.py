@@ -115,3 +115,51 @@ def test_stacker_discrete_api_roundtrip():
     last_port = cd.portfolio[:, -1].cpu().numpy()
     np.testing.assert_allclose(last_port, orc.obs_port[orc.head].T, rtol=1e-9, atol=1e-12)
 
+
+
+@pytest.mark.parametrize("norm", NORMS)
+@pytest.mark.parametrize("name", ["pairs", "returns"])
+def test_stacker_variants_match_reference(name, norm):
+    """StackerDiscretePairs / StackerDiscreteReturns (preprocessor.py:295-333) against the reference's own classes
+    (tests/golden/stackers.npz) and, at a larger shape, against the numpy restatement."""
+    from madigan_b200 import _abi as A
+    SK = np.load(os.path.join(GOLD, "stackers.npz"))
+    prices, steps = SK[f"{name}_prices"], SK["steps"]
+    ref = SK[f"{name}_out_{norm}"]
+    k, nF = ref.shape[1], prices.shape[1]
+    xf = A.XFORM_PAIR_RATIO if name == "pairs" else A.XFORM_RETURNS
+    env = make_env(5, nF, k)
+    for idx, t in enumerate(steps):
+        load_ring(env, np.repeat(prices[:t + 1, :, None], 5, axis=2), t)
+        got = env.window(norm, dtype=torch.float64, transform=xf).cpu().numpy()
+        assert got.shape == (5,) + ref[idx].shape
+        for e in range(5):
+            np.testing.assert_allclose(got[e], ref[idx], rtol=1e-9, atol=1e-12, equal_nan=True)
+    # random ring, channels-first and fp32 too
+    rng = np.random.default_rng(31)
+    N, k2, nF2 = 130, 64, (2 if name == "pairs" else 16)
+    env = make_env(N, nF2, k2)
+    R = k2 + 5
+    rows = np.abs(10 + np.cumsum(rng.standard_normal((R, nF2, N)) * .2, axis=0)) + .1
+    load_ring(env, rows, R - 1)
+    want = np.stack([py_oracle.stack_window(w, norm, name) for w in rows[R - k2:].transpose(2, 0, 1)])
+    got = env.window(norm, dtype=torch.float64, transform=xf).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11, equal_nan=True)
+    got_cf = env.window(norm, dtype=torch.float32, channels_first=True, transform=xf).cpu().numpy()
+    np.testing.assert_allclose(got_cf, want.transpose(0, 2, 1).astype(np.float32), rtol=2e-6, atol=1e-6, equal_nan=True)
+
+
+def test_stacker_variant_classes():
+    from madigan_b200.utils.preprocessor import StackerDiscretePairs, StackerDiscreteReturns, make_preprocessor
+    env = make_env(9, 2, 8)
+    env.reset(fill_history=True)
+    pre = make_preprocessor({"preprocessor_type": "StackerDiscretePairs",
+                             "preprocessor_config": {"window_length": 8, "norm": True, "norm_type": "lookback"}}, 2)
+    assert isinstance(pre, StackerDiscretePairs) and pre.feature_output_shape == (8, 1)
+    pre.sync(env)
+    st = pre.current_data()
+    assert st.price.shape == (9, 8, 1) and st.portfolio.shape == (9, 8, 3) and st.timestamp.shape == (9, 8)
+    ret = StackerDiscreteReturns(8, 2, norm=False)
+    ret.sync(env)
+    st = ret.current_data()
+    assert st.price.shape == (9, 8, 1) and st.portfolio.shape == (9, 7, 3) and st.timestamp.shape == (9, 7)
