@@ -470,7 +470,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slabs", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

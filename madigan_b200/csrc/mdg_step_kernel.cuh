@@ -422,8 +422,8 @@ __device__ __forceinline__ void normal_block(uint32_t gid, uint32_t blk, uint32_
 //     wave (that launch is latency-bound: a second wave would cost as much as the first);
 //   168 registers -> 3 blocks per SM, no spills: best throughput when there are many waves (>= 262,144 envs).
 // (64-thread blocks x 7 per SM at 144 registers were measured slower than either.)
-template <bool PAIRS, int BS, int MINB, bool ACTIONS>
-__global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ StepArgs a) {
+template <bool PAIRS, int BS, bool ACTIONS>
+__device__ __forceinline__ void step_body(const StepArgs& a) {
   // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff (and, in the
   // all-pairs kernel, this step's normals before they are consumed; see stash_normal_row)
   extern __shared__ double stash[];
@@ -697,6 +697,11 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
     if (a.R.nstep > 1) S.nstep_len[e] = len_after;
     a.IO.n_popped[e] = n_popped;
   }
+}
+
+template <bool PAIRS, int BS, int MINB, bool ACTIONS>
+__global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ StepArgs a) {
+  step_body<PAIRS, BS, ACTIONS>(a);
 }
 
 // host side: is every asset part of an OUPair laid out (role0, role1) with in-order noise slots?
