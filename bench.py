@@ -250,11 +250,19 @@ def run_ours(args):
     n_str = max(1, min(args.streams, slabs))
     streams = [torch.cuda.Stream(dev) for _ in range(n_str)]
 
+    fixed_streams = slabs % n_str == 0  # then slab i always runs on stream i % n_str: bind it once
+    if fixed_streams:
+        for i_, e_ in enumerate(envs):
+            e_.bind_stream(streams[i_ % n_str])
+
     def step_slab(i, acts_i):
         env = envs[i % slabs]
-        with torch.cuda.stream(streams[i % n_str]):
-            env.step(acts_i)                                           # the fused step kernel (dominant kernel)
-            env._reset_launch(env.t["done"], WINDOW, True, None, None)  # masked auto-reset + history fill
+        # the fused step kernel (dominant kernel) + masked auto-reset with history fill: one host call
+        if fixed_streams:
+            env.step(acts_i, auto_reset=True)
+        else:
+            with torch.cuda.stream(streams[i % n_str]):
+                env.step(acts_i, auto_reset=True)
 
     def fork(ev):
         for st in streams:
@@ -299,6 +307,8 @@ def run_ours(args):
 
     # ---- the dominant kernel alone (roofline): the step kernel of consecutive slabs back to back on ONE stream,
     # CUDA events around every launch, resets outside the event pairs
+    for e_ in envs:
+        e_.bind_stream(None)  # from here on the launches follow torch's current stream again
     KK = min(K, 200)
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KK)]
     for i in range(KK):

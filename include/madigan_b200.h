@@ -256,6 +256,13 @@ int mdg_reset_ws(const MdgParams *params, const MdgState *state, const MdgStepIO
                  void *workspace, int64_t workspace_bytes);
 int64_t mdg_reset_workspace_bytes(const MdgParams *params, int64_t n_envs, int fill_ticks);
 
+/* The agent loop's `step; if done: reset + initialize_history` (offpolicy_q.py:93-99,140-153) as ONE host call:
+ * mdg_step, then mdg_reset_ws masked by the step's own io->done.  Same launches as the two calls, one trip
+ * through the binding (the host side of a step is then cheaper than the device side at 65,536 envs). */
+int mdg_step_autoreset(const MdgParams *params, const MdgReward *reward, const MdgState *state,
+                       const MdgStepIO *io, const MdgLaunch *launch, int fill_ticks, int clear_nstep,
+                       void *workspace, int64_t workspace_bytes);
+
 /* Constructor state (Env.h:139-165 before the first tick): generator start values,
  * empty ledger, cash=init_cash, timestamp=0, shaper state zero. */
 int mdg_init_state(const MdgParams *params, const MdgReward *reward, const MdgState *state,

@@ -103,6 +103,8 @@ SYMBOLS = {
     "mdg_reset_ws": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch), C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p, C.c_int64]),
     "mdg_reset_workspace_bytes": (C.c_int64, [_P(MdgParams), C.c_int64, C.c_int]),
+    "mdg_step_autoreset": (C.c_int, [_P(MdgParams), _P(MdgReward), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch),
+                                     C.c_int, C.c_int, C.c_void_p, C.c_int64]),
     "mdg_init_state": (C.c_int, [_P(MdgParams), _P(MdgReward), _P(MdgState), _P(MdgLaunch)]),
     "mdg_refresh_folds": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgLaunch)]),
     "mdg_derived": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgDerived), _P(MdgLaunch)]),

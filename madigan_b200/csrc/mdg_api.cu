@@ -537,6 +537,16 @@ extern "C" int mdg_reset_ws(const MdgParams* P, const MdgState* S, const MdgStep
   return cuda_err(cudaGetLastError(), "mdg_reset_ws launch");
 }
 
+extern "C" int mdg_step_autoreset(const MdgParams* P, const MdgReward* R, const MdgState* S, const MdgStepIO* IO,
+                                  const MdgLaunch* L, int fill_ticks, int clear_nstep, void* workspace,
+                                  int64_t workspace_bytes) {
+  int rc = mdg_step(P, R, S, IO, L);
+  if (rc) return rc;
+  MdgStepIO io = *IO;  // the reset draws from Philox (no injected stream) and takes no units
+  io.units = nullptr; io.normals = nullptr; io.uniforms = nullptr; io.actions = nullptr;
+  return mdg_reset_ws(P, S, &io, L, IO->done, fill_ticks, clear_nstep, workspace, workspace_bytes);
+}
+
 extern "C" int mdg_init_state(const MdgParams* P, const MdgReward* R, const MdgState* S, const MdgLaunch* L) {
   int rc = check_common(P, L);
   if (rc) return rc;

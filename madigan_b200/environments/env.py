@@ -74,12 +74,12 @@ _RESET_WS = {}
 _RESET_NEED = {}
 
 
-def _reset_workspace(lib_, P, n_envs, fill_ticks, device):
+def _reset_workspace(lib_, P, n_envs, fill_ticks, device, stream_ptr=None):
     nk = (P.n_normals, n_envs, fill_ticks)
     need = _RESET_NEED.get(nk)
     if need is None:
         need = _RESET_NEED[nk] = int(lib_.mdg_reset_workspace_bytes(C.byref(P), n_envs, fill_ticks))
-    key = (device.index, _raw_stream(device.index))
+    key = (device.index, _raw_stream(device.index) if stream_ptr is None else stream_ptr)
     ws = _RESET_WS.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=device)
@@ -170,7 +170,11 @@ class Env:
             setattr(IO, name, self.t[name].data_ptr())
         self._IO = IO
         self._d = None
+        self._stream, self._stream_ptr = None, None
         self._L = A.MdgLaunch(n_envs=N, env_offset=self.env_offset, seed=self.seed, window=k)
+        # byref() objects of the persistent descriptors, built once (each byref() call costs ~0.3 us)
+        self._pP, self._pR, self._pS = C.byref(self.P), C.byref(self.R), C.byref(self._S)
+        self._pIO, self._pL = C.byref(self._IO), C.byref(self._L)
         # zero-copy (N, nA) views of the [nA][N] output tensors, built once
         t = self.t
         self._resp = BrokerResponse("", t["timestamp"], t["trans_price"].t(), t["trans_units"].t(),
@@ -190,8 +194,16 @@ class Env:
         L.nstep_pos = self._gstep % self.R.nstep
         L.seed = self.seed
         L.env_offset = self.env_offset
-        L.stream = _raw_stream(self.device.index)
+        L.stream = self._stream_ptr if self._stream_ptr is not None else _raw_stream(self.device.index)
         return L
+
+    def bind_stream(self, stream):
+        """Pin this env's launches to ``stream`` (a torch.cuda.Stream; None = torch's current stream again).
+        A driver that steps several slabs round-robin, one stream per slab, then needs no stream context manager
+        per call (which costs more host time than the step itself); inputs must already be on the device, or be
+        copied by the caller on that stream."""
+        self._stream = stream
+        self._stream_ptr = None if stream is None else stream.cuda_stream
 
     def _device_ctx(self):
         """`with` context selecting this env's device only when it is not already current (saves ~5 us per call)."""
@@ -245,7 +257,7 @@ class Env:
             m = m.to(device=self.device, dtype=torch.uint8).contiguous()
             if tuple(m.shape) != (self.N,):
                 raise ValueError(f"mask must have shape ({self.N},)")
-        ws = _reset_workspace(self._lib, self.P, self.N, int(fill_ticks), self.device)
+        ws = _reset_workspace(self._lib, self.P, self.N, int(fill_ticks), self.device, self._stream_ptr)
         check(self._lib.mdg_reset_ws(C.byref(self.P), C.byref(self._S), C.byref(io), C.byref(self._launch()),
                                      None if m is None else m.data_ptr(), int(fill_ticks), int(clear_nstep),
                                      ws.data_ptr(), ws.numel()))
@@ -318,8 +330,15 @@ class Env:
             self.head = (self.head + 1) % self.k
             self.n_valid = min(self.k, self.n_valid + 1)
             L = self._launch(mode, asset_idx)
-            check(self._lib.mdg_step(C.byref(self.P), C.byref(self.R), C.byref(self._S), C.byref(io), C.byref(L)))
-            self.launches += 1
+            if auto_reset and keep is None:  # step + masked reset + history fill in one trip through the binding
+                ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr)
+                check(self._lib.mdg_step_autoreset(self._pP, self._pR, self._pS, self._pIO, self._pL, self.k, 1,
+                                                   ws.data_ptr(), ws.numel()))
+                self.launches += 2 + 2 * max(1, -(-self.N // 65536))
+                auto_reset = False
+            else:
+                check(self._lib.mdg_step(self._pP, self._pR, self._pS, self._pIO, self._pL))
+                self.launches += 1
             if mode != A.MODE_HOLD and self.R.shaper != A.SHAPER_OFF:
                 self._gstep += 1
             self._version += 1
@@ -361,7 +380,14 @@ class Env:
                 self.n_valid = min(self.k, self.n_valid + 1)
                 L = self._launch(A.MODE_MULTI, 0)
                 L.action_atoms, L.unit_size = int(action_atoms), float(unit_size)
-                check(self._lib.mdg_step(C.byref(self.P), C.byref(self.R), C.byref(self._S), C.byref(io), C.byref(L)))
+                if auto_reset and keep is None:
+                    ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr)
+                    check(self._lib.mdg_step_autoreset(self._pP, self._pR, self._pS, self._pIO, self._pL, self.k, 1,
+                                                       ws.data_ptr(), ws.numel()))
+                    self.launches += 1 + 2 * max(1, -(-self.N // 65536))
+                    auto_reset = False
+                else:
+                    check(self._lib.mdg_step(self._pP, self._pR, self._pS, self._pIO, self._pL))
             finally:
                 io.actions = None
             self.launches += 1
