@@ -419,6 +419,10 @@ def run_ours(args):
             "gpu_launches": launches, "host_issue_ms_per_step": t_issue, "clocks": clocks,
             "episode_stats": parallel.summarize_stats(stats, N_ASSETS),
         }
+        es = line["episode_stats"]
+        # share of the envs that finished (and were reset with a 64-tick history fill) in the last step: the random
+        # policy ruins ~3 % of the envs per step early on and fewer once the survivors' equity has grown
+        line["config"]["done_rate_last_step"] = es["n_done"] / max(es["n_envs"], 1)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()
