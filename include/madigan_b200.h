@@ -228,7 +228,7 @@ enum MdgNorm {
 
 int mdg_abi_version(void);
 /* sizeof of the ABI structs as compiled: 0 MdgAssetGen 1 MdgParams 2 MdgReward 3 MdgState 4 MdgStepIO
- * 5 MdgLaunch 6 MdgDerived; -1 for an unknown index (lets a binding verify its struct mirror) */
+ * 5 MdgLaunch 6 MdgDerived 7 MdgWindow 8 MdgReplay 9 MdgReplayBatch; -1 for an unknown index (lets a binding verify its struct mirror) */
 int mdg_sizeof(int which);
 const char *mdg_last_error(void);
 
@@ -305,6 +305,54 @@ int mdg_materialise_time(const int64_t *timestamp, int64_t n_envs, int32_t n_val
  * and count of non-flat positions): the vector that is all-reduced across GPUs. */
 int mdg_episode_stats(const MdgParams *params, const MdgState *state, const MdgStepIO *io,
                       const MdgLaunch *launch, double *out /* device, zeroed by the call */);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Device-side n-step replay ingest: ReplayBuffer.add + NStepBuffer.pop_nstep_sarsd
+ * (utils/buffers/replay_buffer.py:68-92, nstep_buffer.py:336-361) for every env of the slab, and
+ * ReplayBuffer._sample (replay_buffer.py:110-132) as a gather -- observations never leave HBM.
+ *
+ * Observations are stored ONCE per step: obs slot t % depth holds, for every env, the window an agent sees after
+ * step t ((N,k,F) as written by mdg_materialise_window, plus the newest portfolio row).  A transition is a record
+ * (env, slot of its state, slot of its next_state, action, n-step shaped reward, done) in a global ring; the
+ * step kernel has already produced the popped rewards (io.shaped_reward / io.n_popped) with the reference's
+ * full-buffer / drain-on-done semantics, so the pops of step t are
+ *     state = obs[t - L], action = a[t - L + 1], next_state = obs[t], done = done[t],  L = len, len-1, ...
+ * Deviation (documented): with auto-reset the window of a finished env is materialised after its reset, so the
+ * next_state of a terminal transition is the first observation of the next episode (the bootstrap is masked by
+ * `done`); that same slot is, correctly, the state of the next episode's first transition. */
+typedef struct MdgReplay {
+  /* transition ring, capacity `capacity` records, structure of arrays */
+  int32_t *t_env, *t_state_slot, *t_next_slot; /* [capacity] */
+  int64_t *t_state_step;                       /* [capacity] step index of the state's observation (staleness check) */
+  uint8_t *t_done;                             /* [capacity] */
+  double *t_reward;                            /* [capacity][ra] */
+  double *t_action;                            /* [capacity][n_action] */
+  unsigned long long *cursor;                  /* [1] transitions appended so far (monotonic) */
+  double *act_ring;                            /* [nstep][N][n_action] actions of the last nstep steps */
+  int64_t capacity;
+  int32_t depth;                               /* observation slots */
+  int32_t nstep, ra, n_action;
+} MdgReplay;
+
+/* After step `step` (0-based count of agent steps of this slab): records `action` (N, n_action) and appends the
+ * transitions popped by that step.  nstep_len = MdgState.nstep_len AFTER the step (NULL when nstep == 1). */
+int mdg_replay_append(const MdgReplay *rp, int64_t n_envs, int64_t step, const double *action,
+                      const double *shaped_reward /* [nstep][ra][N] */, const int32_t *n_popped,
+                      const int32_t *nstep_len, const uint8_t *done, void *stream);
+
+/* Draw `batch` transition indices uniformly from the stored, non-stale transitions (Philox keyed by seed, draw)
+ * and gather the batch.  obs_price: [depth][N][k*F] (dtype out_dtype), obs_port: [depth][N][n_port] f64.
+ * Outputs (device): idx [batch] int64, state/next price (batch, k*F), state/next portfolio row (batch, n_port),
+ * action (batch, n_action), reward (batch, ra), done (batch) uint8. */
+typedef struct MdgReplayBatch {
+  int64_t *idx;
+  void *state_price, *next_price;
+  double *state_port, *next_port, *action, *reward;
+  uint8_t *done;
+} MdgReplayBatch;
+int mdg_replay_sample(const MdgReplay *rp, int64_t n_envs, int64_t cur_step, const void *obs_price,
+                      const double *obs_port, int32_t window_elems, int32_t n_port, int32_t obs_dtype,
+                      int64_t batch, uint64_t seed, uint64_t draw, const MdgReplayBatch *out, void *stream);
 
 #ifdef __cplusplus
 }

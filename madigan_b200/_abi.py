@@ -93,6 +93,18 @@ class MdgDerived(C.Structure):
 
 # every symbol include/madigan_b200.h declares: name -> (restype, argtypes)
 _P = C.POINTER
+class MdgReplay(C.Structure):
+    _fields_ = [(n, _dp) for n in ("t_env", "t_state_slot", "t_next_slot", "t_state_step", "t_done", "t_reward",
+                                   "t_action", "cursor", "act_ring")] + \
+               [("capacity", C.c_int64), ("depth", C.c_int32), ("nstep", C.c_int32), ("ra", C.c_int32),
+                ("n_action", C.c_int32)]
+
+
+class MdgReplayBatch(C.Structure):
+    _fields_ = [(n, _dp) for n in ("idx", "state_price", "next_price", "state_port", "next_port", "action",
+                                   "reward", "done")]
+
+
 SYMBOLS = {
     "mdg_abi_version": (C.c_int, []),
     "mdg_last_error": (C.c_char_p, []),
@@ -109,6 +121,10 @@ SYMBOLS = {
     "mdg_refresh_folds": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgLaunch)]),
     "mdg_derived": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgDerived), _P(MdgLaunch)]),
     "mdg_materialise_window": (C.c_int, [_P(MdgWindow)]),
+    "mdg_replay_append": (C.c_int, [_P(MdgReplay), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mdg_replay_sample": (C.c_int, [_P(MdgReplay), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, _P(MdgReplayBatch), C.c_void_p]),
     "mdg_materialise_time": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "mdg_episode_stats": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch),
                                     C.c_void_p]),
@@ -124,4 +140,5 @@ def bind(lib):
     return lib
 
 
-STRUCTS = (MdgAssetGen, MdgParams, MdgReward, MdgState, MdgStepIO, MdgLaunch, MdgDerived, MdgWindow)  # mdg_sizeof order
+STRUCTS = (MdgAssetGen, MdgParams, MdgReward, MdgState, MdgStepIO, MdgLaunch, MdgDerived, MdgWindow, MdgReplay,
+           MdgReplayBatch)  # mdg_sizeof order

@@ -585,6 +585,8 @@ extern "C" int mdg_sizeof(int which) {
     case 5: return (int)sizeof(MdgLaunch);
     case 6: return (int)sizeof(MdgDerived);
     case 7: return (int)sizeof(MdgWindow);
+    case 8: return (int)sizeof(MdgReplay);
+    case 9: return (int)sizeof(MdgReplayBatch);
   }
   return -1;
 }

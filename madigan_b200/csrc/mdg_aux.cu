@@ -7,6 +7,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include "mdg_common.cuh"
 
 namespace mdg {
@@ -157,73 +159,118 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
   // phase 1: coalesced ring reads (consecutive envs), column into smem.  Rows older than the env's last
   // reset are not in the ring: they come from the env-major prefix buffer (prices) or are flat (portfolio).
   if (live) {
-    int slot = slot0;
     long long since = 0x7fffffff;  // ring rows written since the last reset (the newest row always is one)
     if (a.timestamp) since = a.timestamp[e] - a.reset_ts[e] + 1;
-    for (int s = 0; s < nv; ++s) {
-      const int age = nv - 1 - s;
-      double v;
-      if (age < since) v = a.ring[((int64_t)slot * F + f) * a.N + e];
-      else if (a.prefix) v = a.prefix[((int64_t)e * k + (k - 1 - (age - (since - 1)))) * F + f];
-      else v = (f == 0) ? 1. : 0.;  // flat portfolio: ledgerNormedFull == [1, 0, ..., 0]
-      col[s * a.sstride] = v;
-      if (++slot == k) slot = 0;
+    // 16 independent loads in flight per thread (a one-load-per-iteration loop made the kernel latency-bound:
+    // 1.1 ms per 65,536 x 64 x 16 window, profiles/r1_notes.md)
+    constexpr int U = 16;
+    const int Z = blockDim.z, z = threadIdx.z;  // the column's rows are dealt round-robin to Z threads
+    const int isince = since > nv ? nv : (int)since;             // rows with age < isince come from the ring
+    const double* rbase = a.ring + (int64_t)f * a.N + e;         // + slot * rstride
+    const int64_t rstride = (int64_t)F * a.N;
+    // prefix row of age `age`: k - 1 - (age - (since - 1)) = (k - 2 + since) - age
+    const double* pbase = a.prefix ? a.prefix + ((int64_t)e * k + (k - 2 + isince)) * F + f : nullptr;
+    const double flat = (f == 0) ? 1. : 0.;  // flat portfolio: ledgerNormedFull == [1, 0, ..., 0]
+    for (int j0 = 0; z + Z * j0 < nv; j0 += U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = z + Z * (j0 + u);
+        v[u] = 0.;
+        if (s < nv) {
+          const int age = nv - 1 - s;
+          int slot = slot0 + s;
+          if (slot >= k) slot -= k;
+          if (age < isince) v[u] = rbase[slot * rstride];
+          else if (pbase) v[u] = *(pbase - (int64_t)age * F);
+          else v[u] = flat;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = z + Z * (j0 + u);
+        if (s < nv) col[s * a.sstride] = v[u];
+      }
     }
   }
   __syncthreads();
   const int Fe = a.Feff;
   if (a.xform == MDG_XFORM_PAIR_RATIO) {  // price[:, 0] / price[:, 1]  (preprocessor.py:314-315)
-    if (live && f == 0)
+    if (live && f == 0 && threadIdx.z == 0)
       for (int s = 0; s < nv; ++s) col[s * a.sstride] = col[s * a.sstride] / col[s * a.sstride + 1];
     __syncthreads();
   }
 
-  // phase 2: normalise in place
-  if (live && f < Fe) {
-    switch (a.norm) {
-      case MDG_NORM_LOOKBACK: {  // x / x[-1]
-        const double last = col[(nv - 1) * a.sstride];
-        for (int s = 0; s < nv; ++s) col[s * a.sstride] = col[s * a.sstride] / last;
-        break;
+  // phase 2: normalise in place.  The element-wise parts (logs, the final scale/shift) are spread over the Z
+  // threads of a column; only the column statistics (sums in numpy's order) are one thread per column.
+  // Divisions by a per-column constant are multiplications by its reciprocal, logs are mdg_math's fast_log
+  // (observations carry the 1e-9 bar).
+  {
+    const int Z = blockDim.z, z = threadIdx.z;
+    const bool mine = live && f < Fe;
+    double* cpar = tile + (int64_t)a.envs * a.estride + ((int64_t)el * F + f) * 2;  // (shift, scale) per column
+    // 2a: element-wise pre-transform
+    if (mine && (a.norm == MDG_NORM_LOG || a.norm == MDG_NORM_LOG_STANDARD)) {
+      for (int s = z; s < nv; s += Z) {
+        double x = col[s * a.sstride];
+        if (a.norm == MDG_NORM_LOG) x = (x != x) ? x : (x < 1e-5 ? 1e-5 : x);  // log(max(x, 1e-5))
+        col[s * a.sstride] = fast_log(x);
       }
-      case MDG_NORM_LOOKBACK_LOG: {  // log(x / x[-1])
-        const double last = col[(nv - 1) * a.sstride];
-        for (int s = 0; s < nv; ++s) col[s * a.sstride] = log(col[s * a.sstride] / last);
-        break;
-      }
-      case MDG_NORM_LOG:  // log(max(x, 1e-5))
-        for (int s = 0; s < nv; ++s) {
-          const double x = col[s * a.sstride];
-          col[s * a.sstride] = log((x != x) ? x : (x < 1e-5 ? 1e-5 : x));
+    }
+    if (a.norm == MDG_NORM_LOG_STANDARD) __syncthreads();
+    // 2b: column statistics
+    if (mine && z == 0) {
+      double shift = 0., scale = 1.;
+      const bool pw = (Fe == 1);
+      switch (a.norm) {
+        case MDG_NORM_LOOKBACK:      // x / x[-1]
+        case MDG_NORM_LOOKBACK_LOG:  // log(x / x[-1])
+          scale = 1. / col[(nv - 1) * a.sstride];
+          break;
+        case MDG_NORM_STANDARD: {  // nan_to_num((x - mean(0)) / std(0))
+          shift = col_sum<0>(col, nv, a.sstride, 0., pw) / nv;
+          scale = 1. / sqrt(col_sum<1>(col, nv, a.sstride, shift, pw) / nv);
+          break;
         }
-        break;
-      case MDG_NORM_STANDARD: {  // nan_to_num((x - mean(0)) / std(0))
-        const bool pw = (Fe == 1);
-        const double mean = col_sum<0>(col, nv, a.sstride, 0., pw) / nv;
-        const double sd = sqrt(col_sum<1>(col, nv, a.sstride, mean, pw) / nv);
-        for (int s = 0; s < nv; ++s) col[s * a.sstride] = nan_to_num((col[s * a.sstride] - mean) / sd);
-        break;
+        case MDG_NORM_LOG_STANDARD: {  // x = log(x); nan_to_num((x - nanmean) / nanstd)
+          int cnt = 0;
+          for (int s = 0; s < nv; ++s) cnt += (col[s * a.sstride] == col[s * a.sstride]) ? 1 : 0;
+          shift = col_sum<2>(col, nv, a.sstride, 0., pw) / cnt;
+          scale = 1. / sqrt(col_sum<3>(col, nv, a.sstride, shift, pw) / cnt);
+          break;
+        }
+        default:
+          break;
       }
-      case MDG_NORM_LOG_STANDARD: {  // x = log(x); nan_to_num((x - nanmean) / nanstd)
-        const bool pw = (Fe == 1);
-        int cnt = 0;
-        for (int s = 0; s < nv; ++s) {
-          const double x = log(col[s * a.sstride]);
+      cpar[0] = shift; cpar[1] = scale;
+    }
+    const bool scaled = a.norm == MDG_NORM_LOOKBACK || a.norm == MDG_NORM_LOOKBACK_LOG ||
+                        a.norm == MDG_NORM_STANDARD || a.norm == MDG_NORM_LOG_STANDARD;
+    if (scaled) {
+      __syncthreads();
+      // 2c: element-wise finish
+      if (mine) {
+        const double shift = cpar[0], scale = cpar[1];
+        const bool zs = a.norm == MDG_NORM_STANDARD || a.norm == MDG_NORM_LOG_STANDARD;
+        for (int s = z; s < nv; s += Z) {
+          double x = col[s * a.sstride];
+          if (zs) {
+            // (x - mean) / sd with sd == 0: 0/0 -> nan -> 0, c/0 -> +-inf -> +-DBL_MAX, as np.nan_to_num
+            const double d = x - shift;
+            x = nan_to_num(d * scale);
+          } else {
+            x = x * scale;
+            if (a.norm == MDG_NORM_LOOKBACK_LOG) x = fast_log(x);
+          }
           col[s * a.sstride] = x;
-          if (x == x) ++cnt;
         }
-        const double mean = col_sum<2>(col, nv, a.sstride, 0., pw) / cnt;
-        const double sd = sqrt(col_sum<3>(col, nv, a.sstride, mean, pw) / cnt);
-        for (int s = 0; s < nv; ++s) col[s * a.sstride] = nan_to_num((col[s * a.sstride] - mean) / sd);
-        break;
       }
-      default:
-        break;
     }
   }
   if (a.norm == MDG_NORM_EXPANDING) {
     // x / _expanding_mean(x): the gufunc runs over the LAST axis (features), preprocessor.py:72-73,472-491
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+    const int nthr = blockDim.x * blockDim.y * blockDim.z;
     for (int r = tid; r < a.envs * nv; r += nthr) {
       const int re = r / nv, rs = r - re * nv;
       if (e0 + re >= a.N) continue;
@@ -242,20 +289,36 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
   __syncthreads();
 
   // phase 3: contiguous write-out of the block's windows
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y * blockDim.z;
   const int Fo = a.Fout;
   const int per_env = nv * Fo;
-  const int64_t rows = (a.N - e0) < a.envs ? (a.N - e0) : a.envs;
-  const int64_t total = rows * per_env;
-  for (int64_t idx = tid; idx < total; idx += nthr) {
-    const int re = (int)(idx / per_env);
-    const int r = (int)(idx - (int64_t)re * per_env);
-    int s, ff;
-    if (a.layout == MDG_LAYOUT_NKF) { s = r / Fo; ff = r - s * Fo; } else { ff = r / nv; s = r - ff * nv; }
-    const double* tp = tile + (int64_t)re * a.estride + (int64_t)s * a.sstride + ff;
-    const double v = (a.xform == MDG_XFORM_RETURNS) ? tp[1] - tp[0] : tp[0];  // np.diff(price): last axis (:330)
-    const int64_t o = e0 * per_env + idx;
-    if (a.out_dtype == MDG_DTYPE_F32) ((float*)a.out)[o] = (float)v; else ((double*)a.out)[o] = v;
+  const int rows = (int)((a.N - e0) < a.envs ? (a.N - e0) : a.envs);
+  const bool f32 = a.out_dtype == MDG_DTYPE_F32, diff = a.xform == MDG_XFORM_RETURNS;
+  if (a.layout == MDG_LAYOUT_NKF && nthr % Fo == 0) {
+    // thread -> fixed feature, rows advance by nthr / Fo: consecutive threads write consecutive elements and no
+    // index needs a division (a 64-bit div/mod per element made this phase instruction-bound)
+    const int ff = tid % Fo, sstep = nthr / Fo;
+    for (int re = 0; re < rows; ++re) {
+      const double* tp = tile + (int64_t)re * a.estride + ff;
+      const int64_t o0 = (e0 + re) * per_env + ff;
+      for (int sr = tid / Fo; sr < nv; sr += sstep) {
+        const double* q = tp + sr * a.sstride;
+        const double v = diff ? q[1] - q[0] : q[0];  // np.diff(price): last axis (:330)
+        if (f32) ((float*)a.out)[o0 + sr * Fo] = (float)v; else ((double*)a.out)[o0 + sr * Fo] = v;
+      }
+    }
+  } else {
+    for (int re = 0; re < rows; ++re) {
+      for (int r = tid; r < per_env; r += nthr) {
+        int sr, ff;
+        if (a.layout == MDG_LAYOUT_NKF) { sr = r / Fo; ff = r - sr * Fo; } else { ff = r / nv; sr = r - ff * nv; }
+        const double* q = tile + (int64_t)re * a.estride + (int64_t)sr * a.sstride + ff;
+        const double v = diff ? q[1] - q[0] : q[0];
+        const int64_t o = (e0 + re) * per_env + r;
+        if (f32) ((float*)a.out)[o] = (float)v; else ((double*)a.out)[o] = v;
+      }
+    }
   }
 }
 
@@ -403,24 +466,34 @@ extern "C" int mdg_materialise_window(const MdgWindow* w) {
   a.ring = w->ring; a.prefix = w->prefix; a.timestamp = w->timestamp; a.reset_ts = w->reset_ts;
   a.out = w->out; a.N = w->n_envs; a.F = n_feats; a.k = window; a.head = head; a.n_valid = n_valid;
   a.norm = w->norm_type; a.out_dtype = w->out_dtype; a.layout = w->out_layout; a.flat_prefix = w->flat_prefix;
-  // envs per block: power of two, 8..32, about 128-256 threads, tile <= ~96 KB
+  // envs per block: a power of two with about 64 columns per block and two threads per column -- small tiles
+  // (35 KB at 64 x 16), six blocks per SM: measured best at 65,536 x 64 x 16 (profiles/window_cost.py)
   int envs = 32;
-  while (envs > 8 && envs * n_feats > 256) envs >>= 1;
+  while (envs > 1 && envs * n_feats > 64) envs >>= 1;
+  static const int env_override = [] { const char* v = getenv("MDG_WIN_ENVS"); return v ? atoi(v) : 0; }();
+  static const int z_override = [] { const char* v = getenv("MDG_WIN_Z"); return v ? atoi(v) : 0; }();
+  if (env_override) envs = env_override;
   a.sstride = n_feats + 1;  // odd-ish row stride: conflict-free (N,F,k) reads
   for (;;) {
     int es = n_valid * a.sstride;
     es += ((2 - es) % 16 + 16) % 16;  // env stride == 2 (mod 16 doubles): conflict-free column writes
     a.estride = es;
-    if ((size_t)envs * es * sizeof(double) <= 96 * 1024 || envs == 1) break;
+    if (((size_t)envs * es + (size_t)envs * n_feats * 2) * sizeof(double) <= 96 * 1024 || envs == 1) break;
     envs >>= 1;
   }
   a.envs = envs;
-  const size_t smem = (size_t)envs * a.estride * sizeof(double);
+  const size_t smem = ((size_t)envs * a.estride + (size_t)envs * n_feats * 2) * sizeof(double);
   if (smem > 200 * 1024) return set_err(MDG_E_UNSUPPORTED, "window tile does not fit shared memory");
-  cudaError_t ce = cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (ce != cudaSuccess) return cuda_err(ce, "window smem attr");
+  static size_t smem_allowed = 48 * 1024;  // raise the opt-in limit only when a larger tile is first needed
+  if (smem > smem_allowed) {
+    cudaError_t ce = cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return cuda_err(ce, "window smem attr");
+    smem_allowed = smem;
+  }
   const unsigned grid = (unsigned)((w->n_envs + envs - 1) / envs);
-  window_kernel<<<grid, dim3(envs, n_feats), smem, (cudaStream_t)w->stream>>>(a);
+  int zdim = 2;  // threads per column for the data-movement and element-wise phases
+  if (z_override) zdim = z_override;
+  window_kernel<<<grid, dim3(envs, n_feats, zdim), smem, (cudaStream_t)w->stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_materialise_window launch");
 }
 
