@@ -354,3 +354,32 @@ def test_roundtrip_property_full_size():
     assert torch.count_nonzero(env.ledger) == 0
     assert torch.equal(env.cash, torch.full_like(env.cash, 1e6))
     assert torch.count_nonzero(env.t["borrowed"]) == 0
+
+
+def test_step_autoreset_single_call_equals_two_calls():
+    """mdg_step_autoreset (one host call, optionally on a bound stream) == mdg_step + mdg_reset_ws(mask=done)."""
+    from madigan_b200.environments import Env
+    cfg = {"data_source_config": PAIRS8}
+    rw = dict(reward_shaper_config={"reward_shaper": "DSR", "adaptation_rate": .001}, nstep_return=3, reduce_rewards=True)
+    envs = [Env("Composite", 1e6, cfg, n_envs=3000, window=16, seed=99, reward=rw) for _ in range(3)]
+    for e in envs:
+        e.setRequiredMargin(.1); e.setTransactionCost(.02, 0.); e.setSlippage(.001, 0.)
+        e.reset(fill_history=True)
+    side = torch.cuda.Stream()
+    envs[2].bind_stream(side)
+    g = torch.Generator().manual_seed(3)
+    n_done = 0
+    for t in range(60):
+        units = (torch.randint(-1, 2, (3000, 16), generator=g).double() * 40_000.).cuda()
+        envs[0].step(units, auto_reset=True)                      # fused call
+        envs[1].step(units)                                       # two calls
+        envs[1]._reset_launch(envs[1].t["done"], 16, True, None, None)
+        side.wait_stream(torch.cuda.current_stream())
+        envs[2].step(units, auto_reset=True)                      # fused call on its own stream
+        torch.cuda.current_stream().wait_stream(side)
+        n_done += int(envs[0].t["done"].sum())
+        for name in ("price", "ledger", "cash", "timestamp", "reset_ts", "obs_price", "pre_price", "shaped_reward",
+                     "shaper_A", "nstep_len", "done"):
+            a = envs[0].t[name]
+            assert torch.equal(a, envs[1].t[name]) and torch.equal(a, envs[2].t[name]), (t, name)
+    assert n_done > 20
