@@ -53,62 +53,6 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // stream 0 (Box-Muller: lane 0 = r*cos, lane 1 = r*sin), uniform slot s in block s>>1 of stream 1.
 constexpr int kMaxNormals = (3 * MDG_MAX_ASSETS) / 2;  // 3 per OU pair, 1 per other asset
 
-struct GenCtx {
-  const double* z;         // this env's normals for this tick: z[slot * zstride] (shared memory column)
-  int zstride;
-  const double* uniforms;  // [n_uniforms][N] for this tick (validation mode) or nullptr
-  int64_t N, e, gstride;
-  uint32_t gid, k0, k1, t_lo, t_hi;
-};
-
-__device__ __forceinline__ void ctx_init(GenCtx& c, const double* z, int zstride, const double* uniforms,
-                                         const MdgLaunch& L, int64_t e, int64_t tick) {
-  c.z = z;
-  c.zstride = zstride;
-  c.uniforms = uniforms;
-  c.N = L.n_envs;
-  c.gstride = L.n_envs;
-  c.e = e;
-  c.gid = (uint32_t)(L.env_offset + e);
-  c.k0 = (uint32_t)L.seed;
-  c.k1 = (uint32_t)(L.seed >> 32);
-  c.t_lo = (uint32_t)(uint64_t)tick;
-  c.t_hi = (uint32_t)((uint64_t)tick >> 32);
-}
-
-// All normal draws of one env for one tick into a shared-memory column.  A ROLLED loop over
-// Philox blocks: one copy of Philox + Box-Muller in the instruction stream (the first version
-// inlined it at every draw site and the kernel became I-cache bound, profiles/r1_notes.md).
-__device__ __forceinline__ void fill_normals(double* zcol, int zstride, int n_normals, const double* normals,
-                                             const GenCtx& c) {
-  if (normals) {  // validation mode: injected stream [n_normals][N]
-    for (int s = 0; s < n_normals; ++s) zcol[s * zstride] = normals[(int64_t)s * c.N + c.e];
-    return;
-  }
-  const int nb = (n_normals + 1) >> 1;
-#pragma unroll 4
-  for (int b = 0; b < nb; ++b) {
-    uint64_t x0, x1;
-    philox4x32_10(c.gid, (uint32_t)b, c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
-    const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;  // (0,1)
-    const double u2 = (double)(x1 >> 11) * 0x1.0p-53;          // [0,1)
-    const double r = fast_sqrt_pos(-2.0 * fast_log_pos(u1));
-    double sn, cs;
-    fast_sincos_2pi(u2, sn, cs);
-    zcol[(2 * b) * zstride] = r * cs;
-    if (2 * b + 1 < n_normals) zcol[(2 * b + 1) * zstride] = r * sn;
-  }
-}
-
-__device__ __forceinline__ double draw_normal(const GenCtx& c, int slot) { return c.z[slot * c.zstride]; }
-
-static __device__ __noinline__ double draw_uniform(const GenCtx& c, int slot) {
-  if (c.uniforms) return c.uniforms[(int64_t)slot * c.N + c.e];
-  uint64_t x0, x1;
-  philox4x32_10(c.gid, (1u << 16) | (uint32_t)(slot >> 1), c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
-  return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
-}
-
 // Draw source of the reset kernel: normals computed on demand (one Box-Muller block cached), so that
 // different lanes can fast-forward different generator groups of different envs.
 struct LazyDraws {
@@ -374,35 +318,6 @@ __device__ __forceinline__ double gen_start(const MdgAssetGen& g, double* __rest
   return 0.;
 }
 
-// ---------------------------------------------------------------------------
-// Portfolio in registers.  CAP = compile-time capacity, na = live assets (== CAP when EXACT).
-// ---------------------------------------------------------------------------
-template <int CAP>
-struct Port {
-  double price[CAP], led[CAP], mep[CAP], bm[CAP];
-  double cash;
-};
-
-// The four left-to-right folds every accounting quantity is made of
-// (Portfolio.cpp:180-182 assetValue, :185 meanEntry.ledger, :207-209 borrowedMargin, :192-196 short entry value)
-template <int CAP, bool EXACT>
-__device__ __forceinline__ void port_sums(const Port<CAP>& q, int na, double& av, double& ml, double& bms,
-                                          double& se) {
-  av = q.led[0] * q.price[0];
-  ml = q.mep[0] * q.led[0];
-  bms = q.bm[0];
-  se = q.led[0] * (q.mep[0] * (q.led[0] < 0. ? 1. : 0.));
-#pragma unroll
-  for (int j = 1; j < CAP; ++j) {
-    if (EXACT || j < na) {
-      av = av + q.led[j] * q.price[j];
-      ml = ml + q.mep[j] * q.led[j];
-      bms = bms + q.bm[j];
-      se = se + q.led[j] * (q.mep[j] * (q.led[j] < 0. ? 1. : 0.));
-    }
-  }
-}
-
 // Portfolio::checkRisk() :243-252 from the folds
 __device__ __forceinline__ bool margin_call(double cash, double av, double ml, double bms, double se,
                                             double maintM) {
@@ -413,83 +328,6 @@ __device__ __forceinline__ bool margin_call(double cash, double av, double ml, d
   const double balance = cash + se;
   if ((balance + pnl) <= -marginRequired) return true;
   return false;
-}
-
-// Broker::handleTransaction(port, i, units) Broker.cpp:124-142 with Portfolio::checkRisk(i,units)
-// :254-279 and Portfolio::handleTransaction :284-323 for asset I.
-// I must be a compile-time constant after unrolling (the portfolio lives in registers).
-template <int CAP, bool EXACT>
-__device__ __forceinline__ int broker_transaction(Port<CAP>& q, int na, const MdgParams& P, const int I,
-                                                  double units, double& tp, double& tu, double& tc) {
-  tp = 0.;
-  tu = 0.;
-  tc = 0.;
-  if (!(units != 0.)) return MDG_RISK_GREEN;
-  const double price = q.price[I];
-  double cur = q.led[I];
-  // ---- Portfolio::checkRisk(i, units)
-  int risk = MDG_RISK_GREEN;
-  const bool opposite = (signbit(units) != 0) != (signbit(cur) != 0);
-  if (!opposite || units > -1 * cur) {
-    double av, ml, bms, se;
-    port_sums<CAP, EXACT>(q, na, av, ml, bms, se);
-    const double pnl = av - ml;
-    const double balance = q.cash + se;
-    const double availableMargin = (balance + pnl) / P.required_margin;
-    if (opposite) {
-      const double excess = units + cur;
-      if (availableMargin <= fabs(price * excess) || balance <= 0.) risk = MDG_RISK_INSUFF_MARGIN;
-    } else {
-      if (margin_call(q.cash, av, ml, bms, se, P.maintenance_margin)) {
-        risk = MDG_RISK_MARGIN_CALL;
-      } else {
-        const double cashAmount = price * units;
-        if (availableMargin <= fabs(cashAmount) || balance <= 0.) risk = MDG_RISK_INSUFF_MARGIN;
-      }
-    }
-  }
-  if (risk != MDG_RISK_GREEN) return risk;
-  // ---- Broker::applySlippage / getTransactionCost  Broker.cpp:171-178
-  const double slippage = (price * P.slippage_rel) + P.slippage_abs;
-  const double transactionPrice = units < 0 ? (price - slippage) : (price + slippage);
-  const double transactionCost = fabs(units * price) * P.tcost_rel + P.tcost_abs;
-  tp = transactionPrice;
-  tu = units;
-  tc = transactionCost;
-  // ---- Portfolio::handleTransaction  Portfolio.cpp:284-323
-  double mep = q.mep[I];
-  if (opposite) {
-    if (fabs(units) > fabs(cur)) {
-      units += cur;
-      q.cash += cur * transactionPrice;
-      cur = 0.;
-      mep = transactionPrice;
-    }
-  } else {
-    mep += (transactionPrice - mep) * (units / (units + cur));
-  }
-  const double amount = transactionPrice * units;
-  const double marginToUse = amount * P.required_margin;
-  const double marginToBorrow = amount - marginToUse;
-  double bm = q.bm[I];
-  bm += marginToBorrow;
-  q.cash -= (marginToUse + transactionCost);
-  cur += units;
-  if (fabs(cur) < 0.000001) {
-    mep = 0.;
-    if (bm > 0.) {
-      q.cash -= bm;
-      bm = 0.;
-    }
-  }
-  if (bm < 0.) {
-    q.cash -= bm;
-    bm = 0.;
-  }
-  q.led[I] = cur;
-  q.mep[I] = mep;
-  q.bm[I] = bm;
-  return MDG_RISK_GREEN;
 }
 
 }  // namespace mdg
