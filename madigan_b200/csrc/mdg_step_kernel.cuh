@@ -268,6 +268,8 @@ struct StepAcc {
   double rAV, rML, rBM, rSE, G;  // running sums (cheap risk bound) and their magnitude bound
   double pav, pml, pbm, pse;     // exact left-to-right folds over the processed assets, old prices
   double nav, gsum;              // exact fold of ledger*new price; magnitude sum for the next step
+  double rprod, inv_prev;        // reduced agent reward accumulated in the asset loop (post_tick)
+  bool reduce_inloop;
   bool bad_risk;
 };
 
@@ -399,7 +401,17 @@ __device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t
   A.nav = (i == 0) ? cur_val : A.nav + cur_val;
   A.gsum += fabs(cur_val);
   st[stash_cur_row<PAIRS>(i, na) * BS] = cur_val;
-  st[stash_pm_row<PAIRS>(i, na) * BS] = prev_val + (tu * tp + tc);  // prev_val + mar_diff, offpolicy_q.py:153-156
+  const double pm = prev_val + (tu * tp + tc);  // prev_val + mar_diff, offpolicy_q.py:153-156
+  if (A.reduce_inloop) {
+    // reduced agent reward (offpolicy_q.py:152-164): sum_j log(max(1 + (cur_j - pm_j)/prevEq, .35)) accumulated as the
+    // log of a product (see the tail) right here, so that pm_j needs no stash row
+    double x = (cur_val - pm) * A.inv_prev;
+    x += 1;
+    x = (x != x) ? x : ((x < .35) ? .35 : x);
+    A.rprod = (i == 0) ? x : A.rprod * x;
+  } else {
+    st[stash_pm_row<PAIRS>(i, na) * BS] = pm;
+  }
 }
 
 // One Philox block -> two standard normals (Box-Muller), the same (block, lane) addressing as draw_normal:
@@ -482,6 +494,9 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   A.pav = A.pml = A.pbm = A.pse = A.nav = A.gsum = 0.;
   A.bad_risk = false;
   const double prevEq = A.cash + A.rAV - A.rBM;  // Env.h:190,208,234
+  A.inv_prev = 1. / prevEq;
+  A.rprod = 1.;
+  A.reduce_inloop = shaping && a.R.reduce_rewards && a.R.shaper != MDG_SHAPER_COSINE;
   // DQN.action_to_transaction (dqn.py:160-179) fused in front of the step: units from discrete actions and the
   // availableMargin of the incoming portfolio (Portfolio.cpp:229-231), one scale for every asset
   // (a template parameter: the three extra live values cost 3 % in the units kernel at its 128-register budget)
@@ -646,7 +661,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
     }
   }
   const int ra = a.R.reduce_rewards ? 1 : na;
-  const double inv_prev = 1. / prevEq;
+  const double inv_prev = A.inv_prev;
   const int len_before = (shaping && a.R.nstep > 1) ? S.nstep_len[e] : 0;
   int len_after = 0, n_popped = 0;
   double rsum = 0., rprod = 1.;
@@ -659,22 +674,18 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       const double dj = a.R.desired_portfolio[j + 1];
       cosv_pp = cosv_pp + w * w; cosv_qq = cosv_qq + dj * dj; cosv_pq = cosv_pq + w * dj;
     }
-    if (shaping && !cosine) {  // agent reward (offpolicy_q.py:152-164); with the cosine shaper see below
+    if (shaping && !cosine && !A.reduce_inloop) {  // per-asset agent rewards (offpolicy_q.py:152-164); cosine: below
       double x = (cur_val - st[stash_pm_row<PAIRS>(j, na) * BS]) * inv_prev;
       x += 1;
-      x = (x != x) ? x : ((x < .35) ? .35 : x);
-      if (a.R.reduce_rewards) {
-        // sum_j log(x_j) as log(prod_j x_j): one log instead of nA (each x_j is in [.35, ~1.x], nA <= 16, so the
-        // product neither overflows nor underflows; the two differ by ~1e-15 absolute -- rewards carry the 1e-9 bar)
-        rprod = (j == 0) ? x : rprod * x;
-      } else {
-        const double r = fast_log(x);
-        gst(&a.IO.agent_reward[(int64_t)j * N + e], r);
-        shaper_add(a, e, j, ra, r, done, len_before, len_after, n_popped);
-      }
+      const double r = fast_log((x != x) ? x : ((x < .35) ? .35 : x));
+      gst(&a.IO.agent_reward[(int64_t)j * N + e], r);
+      shaper_add(a, e, j, ra, r, done, len_before, len_after, n_popped);
     }
   }
-  if (shaping && !cosine && a.R.reduce_rewards) rsum = fast_log(rprod);
+  // reduced reward: sum_j log(x_j) as log(prod_j x_j) -- one log instead of nA (each x_j is in [.35, ~1.x] and
+  // nA <= 16, so the product neither overflows nor underflows; the two differ by ~1e-15 absolute, rewards carry
+  // the 1e-9 bar)
+  if (A.reduce_inloop) rsum = fast_log(A.rprod);
   if (cosine) {  // the PPC term needs the whole portfolio row first (nstep_buffer.py:173-191)
     const double extra = a.R.cosine_temp * (cosv_pq / (sqrt(cosv_pp) * sqrt(cosv_qq)));
 #pragma unroll 1
