@@ -275,6 +275,7 @@ struct StepAcc {
 
 struct StepConsts {
   double reqM, maintM, band_scale;
+  double g1, g2;  // magnitude-bound coefficients of one transaction (tx_asset)
   bool reqM_ok;
 };
 
@@ -353,8 +354,10 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
       A.rML += n_ml - o_ml;
       A.rBM += bm - o_bm;
       A.rSE += ((cur < 0.) ? n_ml : 0.) - o_se;
-      // every new term's magnitude is at most its old magnitude (already in G) plus |units|*(|price|+|tp|)
-      A.G += 3. * (fabs(tu) * (fabs(price) + fabs(transactionPrice))) + fabs(transactionCost);
+      // every new term's magnitude is at most its old magnitude (already in G) plus |units|*(|price|+|tp|), three
+      // terms, plus the cost; with |tp| <= |price|(1+|slip_rel|)+|slip_abs| and |cost| <= |units price||tc_rel|+|tc_abs|
+      // that is |units| * (|price| * g1 + g2) (+ |tc_abs|, added once per asset in the prologue)
+      A.G += fabs(tu) * (fabs(price) * c.g1 + c.g2);
     } else if (risk != MDG_RISK_INSUFF_MARGIN) {
       A.bad_risk = true;
     }
@@ -509,6 +512,9 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   c.maintM = P.maintenance_margin;
   c.reqM_ok = c.reqM > 0. && c.reqM <= 1e6;
   c.band_scale = 1e-9 * (1. + fabs(c.maintM)) * (c.reqM > 1. ? c.reqM : 1.);
+  c.g1 = 6. + 3. * fabs(P.slippage_rel) + fabs(P.tcost_rel);
+  c.g2 = 3. * fabs(P.slippage_abs);
+  A.G += na * fabs(P.tcost_abs);  // the absolute cost of up to nA transactions
 
   const uint32_t gid = (uint32_t)(a.L.env_offset + e);
   const uint32_t k0 = (uint32_t)a.L.seed, k1 = (uint32_t)(a.L.seed >> 32);
