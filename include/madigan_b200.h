@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 7
+#define MDG_ABI_VERSION 8
 #define MDG_MAX_ASSETS 16
 #define MDG_GEN_NPARAM 10
 #define MDG_MAX_NSTEP 64
@@ -196,7 +196,12 @@ typedef struct MdgLaunch {
   int32_t action_atoms; /* MdgStepIO.actions only: number of discrete actions per asset (dqn.py:166) */
   void *stream;        /* cudaStream_t                                        */
   double unit_size;    /* MdgStepIO.actions only: fraction of availableMargin per action unit (dqn.py:164) */
+  int32_t flags;       /* MDG_FLAG_*                                          */
+  int32_t _pad;
 } MdgLaunch;
+/* validation: every risk gate of mdg_step takes the exact left-to-right fold path (the cold path that otherwise
+ * only decides knife-edge cases); ledgers must be identical with and without it */
+#define MDG_FLAG_FORCE_EXACT_GATE 1
 
 /* derived accounting, Portfolio.cpp:140-235,243-252; any pointer may be NULL */
 typedef struct MdgDerived {
@@ -228,7 +233,7 @@ enum MdgNorm {
 
 int mdg_abi_version(void);
 /* sizeof of the ABI structs as compiled: 0 MdgAssetGen 1 MdgParams 2 MdgReward 3 MdgState 4 MdgStepIO
- * 5 MdgLaunch 6 MdgDerived 7 MdgWindow 8 MdgReplay 9 MdgReplayBatch; -1 for an unknown index (lets a binding verify its struct mirror) */
+ * 5 MdgLaunch 6 MdgDerived 7 MdgWindow 8 MdgReplay 9 MdgReplayBatch 10 MdgRewardNorm; -1 for an unknown index (lets a binding verify its struct mirror) */
 int mdg_sizeof(int which);
 const char *mdg_last_error(void);
 
@@ -248,17 +253,20 @@ int mdg_reset(const MdgParams *params, const MdgState *state, const MdgStepIO *i
               const MdgLaunch *launch, const uint8_t *mask, int fill_ticks, int clear_nstep);
 
 /* Same operation with a caller-provided device workspace (at least mdg_reset_workspace_bytes): the
- * resetting envs are compacted into a list, their noise is generated by one perfectly packed kernel
- * and the serial recurrences by another -- several times faster when a few percent of the envs reset
- * every step.  workspace == NULL falls back to mdg_reset.  The workspace holds no state between calls. */
+ * resetting envs are compacted into a list and ONE kernel refills them, a block per listed env (Philox +
+ * Box-Muller of the whole history packed over the block into shared memory, then the serial recurrences of the
+ * env's generator groups on neighbouring lanes) -- many times faster than mdg_reset when a few percent of the
+ * envs reset every step.  workspace == NULL falls back to mdg_reset.  The first 256 bytes of the workspace are a
+ * header (list length, exit ticket) that must be ZERO before the first use; every call leaves it zero again. */
 int mdg_reset_ws(const MdgParams *params, const MdgState *state, const MdgStepIO *io,
                  const MdgLaunch *launch, const uint8_t *mask, int fill_ticks, int clear_nstep,
                  void *workspace, int64_t workspace_bytes);
 int64_t mdg_reset_workspace_bytes(const MdgParams *params, int64_t n_envs, int fill_ticks);
 
-/* The agent loop's `step; if done: reset + initialize_history` (offpolicy_q.py:93-99,140-153) as ONE host call:
- * mdg_step, then mdg_reset_ws masked by the step's own io->done.  Same launches as the two calls, one trip
- * through the binding (the host side of a step is then cheaper than the device side at 65,536 envs). */
+/* The agent loop's `step; if done: reset + initialize_history` (offpolicy_q.py:93-99,140-153) as ONE host call
+ * and TWO launches: the step kernel appends the envs that finished to the workspace's list, the refill kernel
+ * resets exactly those (its grid is sized without knowing the count; blocks past the end of the list exit at once).
+ * `workspace` as for mdg_reset_ws (zeroed header before the first use), required. */
 int mdg_step_autoreset(const MdgParams *params, const MdgReward *reward, const MdgState *state,
                        const MdgStepIO *io, const MdgLaunch *launch, int fill_ticks, int clear_nstep,
                        void *workspace, int64_t workspace_bytes);
@@ -353,6 +361,42 @@ typedef struct MdgReplayBatch {
 int mdg_replay_sample(const MdgReplay *rp, int64_t n_envs, int64_t cur_step, const void *obs_price,
                       const double *obs_port, int32_t window_elems, int32_t n_port, int32_t obs_dtype,
                       int64_t batch, uint64_t seed, uint64_t draw, const MdgReplayBatch *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Streaming reward normalisers (environments/reward_normalization.pyx:14-272): one scalar state machine per env,
+ * fed one raw reward (a log return) per step.  Every pointer is [N] (the queue storage [window][N]).
+ *   SHARPE_FIXED   :61-118   reward / rolling std (Welford add at the head, remove at the tail), min 2 samples
+ *   SORTINO_A      :121-145  the same, negative outputs squared in magnitude
+ *   SORTINO_B / C  :148-218  std over the below-mean rewards only (B squares negative outputs, C does not)
+ *   SHARPE_EWMA    :221-272  reward / exponentially weighted std, alpha = 2 / (window + 1)
+ *   NULL           :49-58    identity */
+enum MdgRewardNormKind {
+  MDG_RN_NULL = 0,
+  MDG_RN_SHARPE_FIXED = 1,
+  MDG_RN_SORTINO_A = 2,
+  MDG_RN_SORTINO_B = 3,
+  MDG_RN_SORTINO_C = 4,
+  MDG_RN_SHARPE_EWMA = 5
+};
+typedef struct MdgRewardNorm {
+  int32_t kind;
+  int32_t window;
+  int64_t n_envs;
+  double alpha;     /* SHARPE_EWMA: 2 / (window + 1)                               */
+  double *buffer;   /* [window][N] the queue (ring storage), fixed-window kinds     */
+  int32_t *size;    /* [N] queue length                                             */
+  int32_t *front;   /* [N] ring slot of the queue front                             */
+  int32_t *count;   /* [N] SORTINO_B/C: samples in the estimate; SHARPE_EWMA: count */
+  double *mean_est; /* [N]                                                          */
+  double *ssq;      /* [N]                                                          */
+  double *ewma, *ewma_old, *ewssq_old, *ewssq, *w1, *w2; /* [N] SHARPE_EWMA        */
+} MdgRewardNorm;
+/* reset(): empty queue and zero estimates for the envs with mask[e] != 0 (mask == NULL: all) */
+int mdg_reward_norm_reset(const MdgRewardNorm *rn, const uint8_t *mask, void *stream);
+/* out[e] = shaper_e.stream(reward[e]) for every env; envs with reset_mask[e] != 0 (nullable) are reset() first --
+ * "needs to be called when environment resets / episode ends" (reward_normalization.pyx:84) */
+int mdg_reward_norm_stream(const MdgRewardNorm *rn, const double *reward, const uint8_t *reset_mask, double *out,
+                           void *stream);
 
 #ifdef __cplusplus
 }

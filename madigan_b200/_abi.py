@@ -5,7 +5,8 @@ checks the struct sizes against the compiled library (``mdg_sizeof``).
 """
 import ctypes as C
 
-MDG_ABI_VERSION = 7
+MDG_ABI_VERSION = 8
+FLAG_FORCE_EXACT_GATE = 1
 XFORM_NONE, XFORM_PAIR_RATIO, XFORM_RETURNS = 0, 1, 2
 MDG_MAX_ASSETS = 16
 MDG_GEN_NPARAM = 10
@@ -73,7 +74,7 @@ class MdgLaunch(C.Structure):
     _fields_ = [("n_envs", C.c_int64), ("env_offset", C.c_int64), ("seed", C.c_uint64),
                 ("window", C.c_int32), ("head", C.c_int32), ("mode", C.c_int32),
                 ("asset_idx", C.c_int32), ("nstep_pos", C.c_int32), ("action_atoms", C.c_int32),
-                ("stream", C.c_void_p), ("unit_size", C.c_double)]
+                ("stream", C.c_void_p), ("unit_size", C.c_double), ("flags", C.c_int32), ("_pad", C.c_int32)]
 
 
 class MdgWindow(C.Structure):
@@ -105,6 +106,15 @@ class MdgReplayBatch(C.Structure):
                                    "reward", "done")]
 
 
+RN_NULL, RN_SHARPE_FIXED, RN_SORTINO_A, RN_SORTINO_B, RN_SORTINO_C, RN_SHARPE_EWMA = range(6)
+
+
+class MdgRewardNorm(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("window", C.c_int32), ("n_envs", C.c_int64), ("alpha", C.c_double)] + \
+               [(n, _dp) for n in ("buffer", "size", "front", "count", "mean_est", "ssq", "ewma", "ewma_old",
+                                   "ewssq_old", "ewssq", "w1", "w2")]
+
+
 SYMBOLS = {
     "mdg_abi_version": (C.c_int, []),
     "mdg_last_error": (C.c_char_p, []),
@@ -128,6 +138,8 @@ SYMBOLS = {
     "mdg_materialise_time": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "mdg_episode_stats": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgLaunch),
                                     C.c_void_p]),
+    "mdg_reward_norm_reset": (C.c_int, [_P(MdgRewardNorm), C.c_void_p, C.c_void_p]),
+    "mdg_reward_norm_stream": (C.c_int, [_P(MdgRewardNorm), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -141,4 +153,4 @@ def bind(lib):
 
 
 STRUCTS = (MdgAssetGen, MdgParams, MdgReward, MdgState, MdgStepIO, MdgLaunch, MdgDerived, MdgWindow, MdgReplay,
-           MdgReplayBatch)  # mdg_sizeof order
+           MdgReplayBatch, MdgRewardNorm)  # mdg_sizeof order

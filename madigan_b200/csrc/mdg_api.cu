@@ -131,16 +131,17 @@ __global__ void __launch_bounds__(kResetBlock) reset_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------
-// reset with a workspace: three packed kernels instead of one block-local kernel.
-//   scan : one thread per env; flagged envs append themselves to a global list (warp-aggregated
-//          atomics), get a fresh portfolio and DataSource::reset().
-//   rng  : one thread per (listed env, tick, Philox block) -> the expensive, dependence-free part
-//          (Philox + Box-Muller) runs perfectly packed at full occupancy, however scattered the
-//          resetting envs are; normals go to an L2-resident scratch [listed env][tick][slot].
-//   recur: one thread per (listed env, generator group): the serial recurrence over the ticks with
-//          the generator state in registers / local memory, reading the scratch, writing ring rows.
-// The host launches ceil(N / cap) rng+recur passes without knowing how many envs reset; passes beyond
-// the list end exit at once.
+// reset with a workspace: a list of the resetting envs + ONE refill kernel.
+//   list  : built by reset_scan_kernel from a mask (explicit Env.reset) or, on the auto-reset path, by the
+//           step kernel itself (its last warp appends the envs whose `done` it has just computed).
+//   refill: one block of 128 threads per listed env (grid-stride; the host sizes the grid without knowing the
+//           count, blocks past the end of the list exit at once).  Per chunk of <= 64 ticks:
+//             phase 1  the dependence-free part -- Philox + Box-Muller of every (tick, block) -- packed over
+//                      the 128 threads into shared memory (the normals never touch global memory);
+//             phase 2  the serial recurrence of each generator group on neighbouring lanes of warp 0, reading
+//                      the normals from shared memory, writing the env's contiguous pre_price rows.
+//           Then the fresh Broker/Account/Portfolio (Env.h:150-165), timestamps and the newest ring row.
+//   The workspace header {count, ticket} is self-cleaning: the last block to leave zeroes it.
 // ---------------------------------------------------------------------------
 struct ResetWsArgs {
   MdgParams P;
@@ -150,15 +151,15 @@ struct ResetWsArgs {
   const uint8_t* mask;
   int fill_ticks;
   int clear_nstep;
-  int* count;       // workspace: number of listed envs
-  int* list;        // workspace: env index of each listed env
-  double* scratch;  // workspace: [cap][fill_ticks][n_normals]
-  int cap;          // listed envs per pass
-  int pass;
+  int* count;   // workspace header: number of listed envs
+  int* ticket;  // workspace header: blocks of the refill kernel that have left
+  int* list;    // workspace: env index of each listed env
+  int chunk;    // ticks per shared-memory chunk
+  int n_groups;
+  int8_t leader[MDG_MAX_ASSETS];
 };
 
 __global__ void __launch_bounds__(256) reset_scan_kernel(const __grid_constant__ ResetWsArgs a) {
-  const MdgParams& P = a.P;
   const int64_t N = a.L.n_envs;
   const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -168,188 +169,143 @@ __global__ void __launch_bounds__(256) reset_scan_kernel(const __grid_constant__
   int base = 0;
   if (lane == (__ffs(ballot) - 1)) base = atomicAdd(a.count, __popc(ballot));
   base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-  if (!flag) return;
-  a.list[base + __popc(ballot & ((1u << lane) - 1u))] = (int)e;
-  const int na = P.n_assets;
-  const int fill = a.fill_ticks;
-  const double cash = P.init_cash;
-  const double eq = cash + 0. - 0.;  // flat portfolio: equity == cash
-  if (a.clear_nstep && a.S.nstep_len) a.S.nstep_len[e] = 0;  // offpolicy_q.py:94
-  a.S.cash[e] = cash;
-  if (a.S.folds) {  // flat portfolio: every fold is a sum of zeros
-    a.S.folds[(int64_t)MDG_FOLD_AV * N + e] = 0.;
-    a.S.folds[(int64_t)MDG_FOLD_ML * N + e] = 0.;
-    a.S.folds[(int64_t)MDG_FOLD_BM * N + e] = 0.;
-    a.S.folds[(int64_t)MDG_FOLD_SE * N + e] = 0.;
-    a.S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(cash);
-  }
-  const long long ts = a.S.timestamp[e];
-  a.S.timestamp[e] = ts + fill;  // the later kernels recover ts as timestamp - fill
-  a.S.reset_ts[e] = ts + fill;
-  a.IO.obs_port[((int64_t)a.L.head * (na + 1)) * N + e] = (cash - 0.) / eq;  // newest row = current state
-  // the per-asset part (DataSource::reset(), zeroed ledger rows) is done by reset_recur_kernel, which has one
-  // thread per (env, generator group) instead of one serial 16-asset loop of dependent loads per flagged env
+  if (flag) a.list[base + __popc(ballot & ((1u << lane) - 1u))] = (int)e;
 }
 
-__global__ void __launch_bounds__(256) reset_rng_kernel(const __grid_constant__ ResetWsArgs a) {
-  const int count = *a.count;
-  const int first = a.pass * a.cap;
-  if (first >= count) return;
-  const int here = (count - first) < a.cap ? (count - first) : a.cap;
-  const int nn = a.P.n_normals, fill = a.fill_ticks;
+constexpr int kFillBlock = 128;
+
+__global__ void __launch_bounds__(kFillBlock) reset_fill_kernel(const __grid_constant__ ResetWsArgs a) {
+  extern __shared__ double zs[];  // [chunk][n_normals]
+  const MdgParams& P = a.P;
+  const int tid = threadIdx.x;
+  const int na = P.n_assets, nn = P.n_normals, nb = (nn + 1) >> 1;
+  const int fill = a.fill_ticks, k = a.L.window, chunk = a.chunk, nlead = a.n_groups;
   const int64_t N = a.L.n_envs;
-  if (a.IO.normals) {  // validation mode: copy the injected stream [tick][slot][env]
-    const int64_t total = (int64_t)here * fill * nn;
-    for (int64_t item = (int64_t)blockIdx.x * 256 + threadIdx.x; item < total; item += (int64_t)gridDim.x * 256) {
-      const int s = (int)(item % nn);
-      const int64_t r = item / nn;
-      const int t = (int)(r % fill), d = (int)(r / fill);
-      const int64_t e = a.list[first + d];
-      a.scratch[item] = a.IO.normals[((int64_t)t * nn + s) * N + e];
-    }
-    return;
-  }
-  const int nb = (nn + 1) >> 1;
+  const int count = *(volatile int*)a.count;
+  const double cash = P.init_cash;
+  const double eq = cash + 0. - 0.;              // flat portfolio: equity == cash
+  const bool eq_plain = eq > 0. && eq < 1e300;   // then (0*p)/eq == 0*p exactly
   const uint32_t k0 = (uint32_t)a.L.seed, k1 = (uint32_t)(a.L.seed >> 32);
-  // one block walks whole envs (grid-stride); inside an env, thread j = tick * nb + block.  All index
-  // arithmetic is 32-bit with a multiply-high reciprocal (64-bit div/mod cost more than the Box-Muller).
-  const uint32_t per_env = (uint32_t)(fill * nb);
-  const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)nb - 1) / (uint32_t)nb);  // ceil(2^32 / nb)
-  for (int d = blockIdx.x; d < here; d += gridDim.x) {
-    const int64_t e = a.list[first + d];
-    const uint32_t gid = (uint32_t)(a.L.env_offset + e);
-    const unsigned long long tick0 = (unsigned long long)(a.S.timestamp[e] - fill);
-    double* zenv = a.scratch + (int64_t)d * fill * nn;
-    for (uint32_t j = threadIdx.x; j < per_env; j += 256) {
-      const uint32_t t = (nb == 1) ? j : __umulhi(j, magic);  // j / nb, exact for j < 2^16 (magic overflows for nb == 1)
-      const uint32_t b = j - t * (uint32_t)nb;
-      const unsigned long long tick = tick0 + t;
-      uint64_t x0, x1;
-      philox4x32_10(gid, b, (uint32_t)tick, (uint32_t)(tick >> 32), k0, k1, x0, x1);
-      const double u1 = ((double)(x0 >> 12) + 0.5) * 0x1.0p-52;
-      const double u2 = (double)(x1 >> 11) * 0x1.0p-53;
-      const double r2 = fast_sqrt_pos(-2.0 * fast_log_pos(u1));
-      double sn, cs;
-      fast_sincos_2pi(u2, sn, cs);
-      double* z = zenv + t * (uint32_t)nn + 2 * b;
-      if ((nn & 1) == 0) {
-        *reinterpret_cast<double2*>(z) = make_double2(r2 * cs, r2 * sn);  // rows of an even length stay 16-byte aligned
-      } else {
-        z[0] = r2 * cs;
-        if (2 * (int)b + 1 < nn) z[1] = r2 * sn;
+  const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)nb - 1) / (uint32_t)(nb > 0 ? nb : 1));  // ceil(2^32 / nb)
+  for (int d = blockIdx.x; d < count; d += gridDim.x) {
+    const int64_t e = a.list[d];
+    const long long ts0 = a.S.timestamp[e];
+    __syncthreads();  // every thread has read the old timestamp (and the previous env's normals are consumed)
+    if (tid == 32) {  // fresh Broker/Account/Portfolio (Env.h:150-165): per-env scalars
+      if (a.clear_nstep && a.S.nstep_len) a.S.nstep_len[e] = 0;  // offpolicy_q.py:94
+      a.S.cash[e] = cash;
+      if (a.S.folds) {  // flat portfolio: every fold is a sum of zeros
+        a.S.folds[(int64_t)MDG_FOLD_AV * N + e] = 0.;
+        a.S.folds[(int64_t)MDG_FOLD_ML * N + e] = 0.;
+        a.S.folds[(int64_t)MDG_FOLD_BM * N + e] = 0.;
+        a.S.folds[(int64_t)MDG_FOLD_SE * N + e] = 0.;
+        a.S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(cash);
+      }
+      a.S.timestamp[e] = ts0 + fill;
+      a.S.reset_ts[e] = ts0 + fill;
+      a.IO.obs_port[((int64_t)a.L.head * (na + 1)) * N + e] = (cash - 0.) / eq;  // newest row = current state
+    }
+    // generator state of group `tid` (warp 0, lanes < nlead) in registers for the whole fast-forward
+    const bool worker = tid < nlead;
+    const int i0 = worker ? a.leader[tid] : 0;
+    const MdgAssetGen& g0 = P.gen[i0];
+    const bool is_pair = g0.type == MDG_GEN_OUPAIR;
+    const int cnt = is_pair ? 2 : 1;
+    const int ngs = gen_state_rows(g0);
+    double pr[2] = {0., 0.}, gsl[4] = {0., 0., 0., 0.};
+    if (worker) {
+      for (int r = 0; r < ngs; ++r) gsl[r] = a.S.gstate[(int64_t)(g0.gslot + r) * N + e];
+      for (int c = 0; c < cnt; ++c) pr[c] = a.S.price[(int64_t)(i0 + c) * N + e];
+      for (int c = 0; c < cnt; ++c) {  // dataSource_->reset() and the empty ledger
+        pr[c] = gen_reset(P.gen[i0 + c], pr[c], gsl, 1);
+        a.S.ledger[(int64_t)(i0 + c) * N + e] = 0.;
+        a.S.mean_entry[(int64_t)(i0 + c) * N + e] = 0.;
+        a.S.borrowed[(int64_t)(i0 + c) * N + e] = 0.;
       }
     }
-  }
-}
-
-__global__ void __launch_bounds__(128) reset_recur_kernel(const __grid_constant__ ResetWsArgs a) {
-  __shared__ int s_leader[MDG_MAX_ASSETS];
-  __shared__ int s_nlead;
-  const MdgParams& P = a.P;
-  const int na = P.n_assets;
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int i = 0; i < na; ++i)
-      if (!(P.gen[i].type == MDG_GEN_OUPAIR && P.gen[i].role == 1)) s_leader[n++] = i;
-    s_nlead = n;
-  }
-  __syncthreads();
-  const int count = *a.count;
-  const int first = a.pass * a.cap;
-  if (first >= count) return;
-  const int here = (count - first) < a.cap ? (count - first) : a.cap;
-  const int nlead = s_nlead;
-  const int nn = P.n_normals, fill = a.fill_ticks, k = a.L.window;
-  const int64_t N = a.L.n_envs;
-  const double cash = P.init_cash;
-  const double eq = cash + 0. - 0.;
-  const bool eq_plain = eq > 0. && eq < 1e300;  // then (0*p)/eq == 0*p exactly
-  const uint32_t total = (uint32_t)here * (uint32_t)nlead;  // < 2^31 * 16 would overflow: here <= cap <= 65536
-  const uint32_t lmagic = (uint32_t)((0x100000000ull + (uint32_t)nlead - 1) / (uint32_t)nlead);
-  // item = d * nlead + l: the groups of one env are neighbouring lanes -> they read one contiguous scratch row
-  for (uint32_t item = blockIdx.x * 128 + threadIdx.x; item < total; item += gridDim.x * 128) {
-    const int d = (nlead == 1) ? (int)item : (int)__umulhi(item, lmagic);  // item / nlead
-    const int l = (int)(item - (uint32_t)d * (uint32_t)nlead);
-    const int64_t e = a.list[first + d];
-    const int i0 = s_leader[l];
-    const int cnt = (P.gen[i0].type == MDG_GEN_OUPAIR) ? 2 : 1;
-    // generator state of this group in registers / local memory for the whole fast-forward
-    double pr[2], gsl[4];
-    const int gslot0 = P.gen[i0].gslot;
-    const int ngs = gslot0 < 0 ? 0
-                    : (P.gen[i0].type == MDG_GEN_TRENDYOU ? 4 : P.gen[i0].type == MDG_GEN_TRENDOU ? 3
-                       : P.gen[i0].type == MDG_GEN_SIMPLETREND ? 2 : 1);
-    for (int r = 0; r < ngs; ++r) gsl[r] = a.S.gstate[(int64_t)(gslot0 + r) * N + e];
-    for (int c = 0; c < cnt; ++c) pr[c] = a.S.price[(int64_t)(i0 + c) * N + e];
-    for (int c = 0; c < cnt; ++c) {  // dataSource_->reset(); fresh Broker/Account/Portfolio (Env.h:150-165)
-      pr[c] = gen_reset(P.gen[i0 + c], pr[c], gsl, 1);
-      a.S.ledger[(int64_t)(i0 + c) * N + e] = 0.;
-      a.S.mean_entry[(int64_t)(i0 + c) * N + e] = 0.;
-      a.S.borrowed[(int64_t)(i0 + c) * N + e] = 0.;
-    }
-    const long long ts0 = a.S.timestamp[e] - fill;
-    const double* zrow = a.scratch + (int64_t)d * fill * nn;
+    const uint32_t gid = (uint32_t)(a.L.env_offset + e);
     double* prow = a.IO.pre_price + ((int64_t)e * k + (k - fill)) * na + i0;
-    if (P.gen[i0].type == MDG_GEN_OUPAIR) {
-      // OUPair::getData (DataSource.cpp:1232-1240) inlined; the next tick's three normals are loaded while
-      // the current tick is computed (the recurrence itself is ~10 dependent flops per tick)
-      const MdgAssetGen& g0 = P.gen[i0];
-      const MdgAssetGen& g1 = P.gen[i0 + 1];
-      const double theta0 = g0.p[0], phi0 = g0.p[1], noise = g0.p[2], theta1 = g1.p[0], phi1 = g1.p[1];
-      const int s_rw = g0.nslot_aux, s_0 = g0.nslot, s_1 = g1.nslot;
-      double m = gsl[0];
-      // chunks of 8 ticks: 24 independent L2 loads in flight, then 8 short dependent updates
-      constexpr int TC = 8;
-#pragma unroll 1
-      for (int t0 = 0; t0 < fill; t0 += TC) {
-        double zr[TC], za[TC], zb[TC];
-#pragma unroll
-        for (int u = 0; u < TC; ++u) {
-          if (t0 + u < fill) {
-            const double* zn = zrow + (int64_t)(t0 + u) * nn;
-            zr[u] = zn[s_rw]; za[u] = zn[s_0]; zb[u] = zn[s_1];
-          }
+    for (int t0 = 0; t0 < fill; t0 += chunk) {
+      const int nt = (fill - t0) < chunk ? (fill - t0) : chunk;
+      if (t0 > 0) __syncthreads();  // the previous chunk's normals are consumed
+      // ---- phase 1: this chunk's normals into shared memory
+      if (a.IO.normals) {  // validation mode: the injected stream [tick][slot][env]
+        for (int j = tid; j < nt * nn; j += kFillBlock) {
+          const int t = j / nn, s_ = j - t * nn;
+          zs[j] = a.IO.normals[((int64_t)(t0 + t) * nn + s_) * N + e];
         }
-#pragma unroll
-        for (int u = 0; u < TC; ++u) {
-          if (t0 + u < fill) {
-            m += m * (zr[u] * noise);
-            pr[0] += (theta0 * (m - pr[0])) + m * (za[u] * phi0);
-            pr[1] += (theta1 * (m - pr[1])) + m * (zb[u] * phi1);
-            double* dst = prow + (int64_t)(t0 + u) * na;
-            if ((na & 1) == 0) {  // 16-byte aligned: one vector store, the env's pairs fill whole sectors together
+      } else {
+        for (uint32_t j = tid; j < (uint32_t)(nt * nb); j += kFillBlock) {
+          const uint32_t t = (nb == 1) ? j : __umulhi(j, magic);  // j / nb, exact for j < 2^16
+          const uint32_t b = j - t * (uint32_t)nb;
+          const unsigned long long tick = (unsigned long long)(ts0 + t0) + t;
+          double za, zb;
+          normal_block(gid, b, (uint32_t)tick, (uint32_t)(tick >> 32), k0, k1, za, zb);
+          double* z = zs + t * (uint32_t)nn + 2 * b;
+          z[0] = za;
+          if (2 * (int)b + 1 < nn) z[1] = zb;
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: the serial recurrences, one generator group per lane
+      if (worker) {
+        if (is_pair) {  // OUPair::getData (DataSource.cpp:1232-1240) inlined
+          const MdgAssetGen& g1 = P.gen[i0 + 1];
+          const double theta0 = g0.p[0], phi0 = g0.p[1], noise = g0.p[2], theta1 = g1.p[0], phi1 = g1.p[1];
+          const int s_rw = g0.nslot_aux, s_0 = g0.nslot, s_1 = g1.nslot;
+          double m = gsl[0];
+#pragma unroll 4
+          for (int t = 0; t < nt; ++t) {
+            const double* zn = zs + t * nn;
+            m += m * (zn[s_rw] * noise);
+            pr[0] += (theta0 * (m - pr[0])) + m * (zn[s_0] * phi0);
+            pr[1] += (theta1 * (m - pr[1])) + m * (zn[s_1] * phi1);
+            double* dst = prow + (int64_t)(t0 + t) * na;
+            if ((na & 1) == 0) {  // 16-byte aligned: the env's pairs fill whole 128-byte lines together
               *reinterpret_cast<double2*>(dst) = make_double2(pr[0], pr[1]);
             } else {
               dst[0] = pr[0];
               dst[1] = pr[1];
             }
           }
+          gsl[0] = m;
+        } else {
+          TickDraws dr;
+          dr.N = N; dr.e = e; dr.gstride = 1;
+          dr.gid = gid; dr.k0 = k0; dr.k1 = k1;
+#pragma unroll 1
+          for (int t = 0; t < nt; ++t) {
+            const long long tick = ts0 + t0 + t;
+            dr.t_lo = (uint32_t)(unsigned long long)tick;
+            dr.t_hi = (uint32_t)((unsigned long long)tick >> 32);
+            dr.z = zs + t * nn;
+            dr.uniforms = a.IO.uniforms ? a.IO.uniforms + (int64_t)(t0 + t) * P.n_uniforms * N : nullptr;
+            double pair_mean = 0.;
+            pr[0] = gen_tick(g0, pr[0], gsl, dr, pair_mean);
+            prow[(int64_t)(t0 + t) * na] = pr[0];
+          }
         }
       }
-      gsl[0] = m;
-    } else {
-      TickDraws dr;
-      dr.N = N; dr.e = e; dr.gstride = 1;
-      dr.gid = (uint32_t)(a.L.env_offset + e);
-      dr.k0 = (uint32_t)a.L.seed; dr.k1 = (uint32_t)(a.L.seed >> 32);
-#pragma unroll 1
-      for (int t = 0; t < fill; ++t) {
-        const long long tick = ts0 + t;
-        dr.t_lo = (uint32_t)(unsigned long long)tick;
-        dr.t_hi = (uint32_t)((unsigned long long)tick >> 32);
-        dr.z = zrow + (int64_t)t * nn;
-        dr.uniforms = a.IO.uniforms ? a.IO.uniforms + (int64_t)t * P.n_uniforms * N : nullptr;
-        double pair_mean = 0.;
-        pr[0] = gen_tick(P.gen[i0], pr[0], gsl, dr, pair_mean);
-        prow[(int64_t)t * na] = pr[0];
+    }
+    if (worker) {
+      for (int c = 0; c < cnt; ++c) {  // newest row = current state, also in the ring
+        a.IO.obs_price[((int64_t)a.L.head * na + i0 + c) * N + e] = pr[c];
+        a.IO.obs_port[((int64_t)a.L.head * (na + 1) + i0 + c + 1) * N + e] = eq_plain ? 0. * pr[c] : (0. * pr[c]) / eq;
       }
+      for (int r = 0; r < ngs; ++r) a.S.gstate[(int64_t)(g0.gslot + r) * N + e] = gsl[r];
+      for (int c = 0; c < cnt; ++c) a.S.price[(int64_t)(i0 + c) * N + e] = pr[c];
     }
-    for (int c = 0; c < cnt; ++c) {  // newest row = current state, also in the ring
-      a.IO.obs_price[((int64_t)a.L.head * na + i0 + c) * N + e] = pr[c];
-      a.IO.obs_port[((int64_t)a.L.head * (na + 1) + i0 + c + 1) * N + e] = eq_plain ? 0. * pr[c] : (0. * pr[c]) / eq;
+  }
+  // self-cleaning header: the last block to leave zeroes the count for the next step kernel
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const int t = atomicAdd(a.ticket, 1);
+    if (t == (int)gridDim.x - 1) {
+      *a.count = 0;
+      *a.ticket = 0;
+      __threadfence();
     }
-    for (int r = 0; r < ngs; ++r) a.S.gstate[(int64_t)(gslot0 + r) * N + e] = gsl[r];
-    for (int c = 0; c < cnt; ++c) a.S.price[(int64_t)(i0 + c) * N + e] = pr[c];
   }
 }
 
@@ -360,9 +316,9 @@ struct InitArgs {
   MdgState S;
   MdgLaunch L;
 };
-__global__ void __launch_bounds__(kBlock) init_kernel(const __grid_constant__ InitArgs a) {
+__global__ void __launch_bounds__(128) init_kernel(const __grid_constant__ InitArgs a) {
   const int64_t N = a.L.n_envs;
-  const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (e >= N) return;
   const int na = a.P.n_assets;
   for (int i = 0; i < na; ++i) {
@@ -394,9 +350,9 @@ struct FoldArgs {
   MdgState S;
   int64_t N;
 };
-__global__ void __launch_bounds__(kBlock) refresh_folds_kernel(const __grid_constant__ FoldArgs a) {
+__global__ void __launch_bounds__(128) refresh_folds_kernel(const __grid_constant__ FoldArgs a) {
   const int64_t N = a.N;
-  const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (e >= N) return;
   double av = 0., ml = 0., bms = 0., se = 0., g = fabs(a.S.cash[e]);
   for (int j = 0; j < a.P.n_assets; ++j) {
@@ -420,7 +376,7 @@ static int check_common(const MdgParams* P, const MdgLaunch* L) {
   if (P->n_assets < 1 || P->n_assets > MDG_MAX_ASSETS)
     return set_err(MDG_E_UNSUPPORTED, "n_assets must be in 1..MDG_MAX_ASSETS (thread-per-env kernels)");
   if (L->n_envs < 0) return set_err(MDG_E_INVALID, "n_envs < 0");
-  if (L->n_envs > (int64_t)2147483647 * kBlock) return set_err(MDG_E_UNSUPPORTED, "n_envs too large");
+  if (L->n_envs > (int64_t)2147483647 * 32) return set_err(MDG_E_UNSUPPORTED, "n_envs too large");
   return MDG_OK;
 }
 
@@ -428,8 +384,8 @@ static int check_common(const MdgParams* P, const MdgLaunch* L) {
 
 using namespace mdg;
 
-extern "C" int mdg_step(const MdgParams* P, const MdgReward* R, const MdgState* S, const MdgStepIO* IO,
-                        const MdgLaunch* L) {
+static int step_impl(const MdgParams* P, const MdgReward* R, const MdgState* S, const MdgStepIO* IO,
+                     const MdgLaunch* L, int* done_count, int* done_list) {
   int rc = check_common(P, L);
   if (rc) return rc;
   if (!S || !IO) return set_err(MDG_E_INVALID, "null state/io");
@@ -459,7 +415,14 @@ extern "C" int mdg_step(const MdgParams* P, const MdgReward* R, const MdgState* 
       return set_err(MDG_E_INVALID, "nstep>1 needs nstep_ring/nstep_len");
     if (L->nstep_pos < 0 || L->nstep_pos >= a.R.nstep) return set_err(MDG_E_INVALID, "bad nstep_pos");
   }
+  a.done_count = done_count;
+  a.done_list = done_list;
   return launch_step(a);
+}
+
+extern "C" int mdg_step(const MdgParams* P, const MdgReward* R, const MdgState* S, const MdgStepIO* IO,
+                        const MdgLaunch* L) {
+  return step_impl(P, R, S, IO, L, nullptr, nullptr);
 }
 
 extern "C" int mdg_reset(const MdgParams* P, const MdgState* S, const MdgStepIO* IO, const MdgLaunch* L,
@@ -482,11 +445,35 @@ extern "C" int mdg_reset(const MdgParams* P, const MdgState* S, const MdgStepIO*
 
 extern "C" int64_t mdg_reset_workspace_bytes(const MdgParams* P, int64_t n_envs, int fill_ticks) {
   if (!P || n_envs < 0) return -1;
-  if (fill_ticks < 1) fill_ticks = 1;
-  // header (count) + list + scratch for min(N, 65536) listed envs per pass
-  const int64_t cap = n_envs < 65536 ? n_envs : 65536;
-  return 256 + 4 * ((n_envs + 63) / 64 * 64) + 8 * cap * (int64_t)fill_ticks * (P->n_normals > 0 ? P->n_normals : 1);
+  (void)fill_ticks;
+  return 256 + 4 * ((n_envs + 63) / 64 * 64);  // header {count, ticket} + list
 }
+
+namespace mdg {
+static int fill_ws_args(ResetWsArgs& a, const MdgParams* P, const MdgState* S, const MdgStepIO* IO, const MdgLaunch* L,
+                        int fill_ticks, int clear_nstep, void* workspace, int64_t workspace_bytes) {
+  const int64_t N = L->n_envs;
+  if (N > 2147483647) return set_err(MDG_E_UNSUPPORTED, "n_envs too large for the reset list");
+  if (workspace_bytes < 256 + 4 * N) return set_err(MDG_E_INVALID, "reset workspace too small (see mdg_reset_workspace_bytes)");
+  a.P = *P; a.S = *S; a.IO = *IO; a.L = *L;
+  a.mask = nullptr; a.fill_ticks = fill_ticks; a.clear_nstep = clear_nstep;
+  a.count = (int*)workspace;
+  a.ticket = (int*)workspace + 1;
+  a.list = (int*)((char*)workspace + 256);
+  a.chunk = fill_ticks < 64 ? fill_ticks : 64;
+  a.n_groups = fill_groups(*P, a.leader);
+  return MDG_OK;
+}
+static int launch_fill(const ResetWsArgs& a, int64_t max_listed) {
+  // the count is on the device: size the grid for the most the list can hold, capped at a few blocks per SM
+  // (grid-stride; blocks past the end of the list only read the count and take their exit ticket)
+  const int64_t cap = 148 * 8;
+  const unsigned grid = (unsigned)(max_listed < cap ? (max_listed > 0 ? max_listed : 1) : cap);
+  const size_t smem = sizeof(double) * (size_t)a.chunk * (size_t)(a.P.n_normals > 0 ? a.P.n_normals : 1);
+  reset_fill_kernel<<<grid, kFillBlock, smem, (cudaStream_t)a.L.stream>>>(a);
+  return cuda_err(cudaGetLastError(), "reset_fill launch");
+}
+}  // namespace mdg
 
 extern "C" int mdg_reset_ws(const MdgParams* P, const MdgState* S, const MdgStepIO* IO, const MdgLaunch* L,
                             const uint8_t* mask, int fill_ticks, int clear_nstep, void* workspace,
@@ -501,50 +488,36 @@ extern "C" int mdg_reset_ws(const MdgParams* P, const MdgState* S, const MdgStep
   if (fill_ticks > L->window) return set_err(MDG_E_INVALID, "fill_ticks > window");
   const int64_t N = L->n_envs;
   if (N == 0) return MDG_OK;
-  if (N > 2147483647) return set_err(MDG_E_UNSUPPORTED, "n_envs too large for the reset list");
-  const int nn = P->n_normals > 0 ? P->n_normals : 1;
-  const int64_t list_bytes = 4 * ((N + 63) / 64 * 64);
-  const int64_t per_env = 8 * (int64_t)fill_ticks * nn;
-  const int64_t cap64 = (workspace_bytes - 256 - list_bytes) / per_env;
-  if (cap64 < 1) return set_err(MDG_E_INVALID, "reset workspace too small (see mdg_reset_workspace_bytes)");
   ResetWsArgs a;
-  a.P = *P; a.S = *S; a.IO = *IO; a.L = *L;
-  a.mask = mask; a.fill_ticks = fill_ticks; a.clear_nstep = clear_nstep;
-  a.count = (int*)workspace;
-  a.list = (int*)((char*)workspace + 256);
-  a.scratch = (double*)((char*)workspace + 256 + list_bytes);
-  a.cap = (int)(cap64 < N ? cap64 : N);
-  a.pass = 0;
+  rc = fill_ws_args(a, P, S, IO, L, fill_ticks, clear_nstep, workspace, workspace_bytes);
+  if (rc) return rc;
+  a.mask = mask;
   cudaStream_t st = (cudaStream_t)L->stream;
-  cudaError_t ce = cudaMemsetAsync(a.count, 0, sizeof(int), st);
+  cudaError_t ce = cudaMemsetAsync(workspace, 0, 256, st);  // an explicit reset does not rely on the header's state
   if (ce != cudaSuccess) return cuda_err(ce, "mdg_reset_ws memset");
   reset_scan_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(a);
-  const int passes = (int)((N + a.cap - 1) / a.cap);
-  const int nb = (P->n_normals + 1) / 2 > 0 ? (P->n_normals + 1) / 2 : 1;
-  // profiling knob (profiles/breakdown.py): stop after the scan (1) or the rng kernel (2); results are then wrong
-  static const int phases = [] { const char* v = getenv("MDG_RESET_PHASES"); return v ? atoi(v) : 3; }();
-  for (int p = 0; p < passes && phases >= 2; ++p) {
-    a.pass = p;
-    // grids sized for a full pass but capped: the kernels are grid-stride and exit at once past the list end
-    unsigned g1 = (unsigned)(a.cap < 148 * 8 ? a.cap : 148 * 8);  // one block per listed env, grid-stride
-    (void)nb;
-    reset_rng_kernel<<<g1 ? g1 : 1, 256, 0, st>>>(a);
-    if (phases < 3) continue;
-    int64_t rec_items = (int64_t)a.cap * P->n_assets;
-    unsigned g2 = (unsigned)((rec_items + 127) / 128 < 148 * 16 ? (rec_items + 127) / 128 : 148 * 16);
-    reset_recur_kernel<<<g2 ? g2 : 1, 128, 0, st>>>(a);
-  }
-  return cuda_err(cudaGetLastError(), "mdg_reset_ws launch");
+  return launch_fill(a, N);
 }
 
 extern "C" int mdg_step_autoreset(const MdgParams* P, const MdgReward* R, const MdgState* S, const MdgStepIO* IO,
                                   const MdgLaunch* L, int fill_ticks, int clear_nstep, void* workspace,
                                   int64_t workspace_bytes) {
-  int rc = mdg_step(P, R, S, IO, L);
+  int rc = check_common(P, L);
   if (rc) return rc;
+  if (!workspace) return set_err(MDG_E_INVALID, "mdg_step_autoreset needs a workspace");
+  if (!S || !IO) return set_err(MDG_E_INVALID, "null state/io");
+  if (!S->reset_ts || !IO->pre_price) return set_err(MDG_E_INVALID, "state.reset_ts / io.pre_price is null");
+  if (fill_ticks < 1) fill_ticks = 1;
+  if (fill_ticks > L->window) return set_err(MDG_E_INVALID, "fill_ticks > window");
+  if (L->n_envs == 0) return MDG_OK;
+  ResetWsArgs a;
   MdgStepIO io = *IO;  // the reset draws from Philox (no injected stream) and takes no units
   io.units = nullptr; io.normals = nullptr; io.uniforms = nullptr; io.actions = nullptr;
-  return mdg_reset_ws(P, S, &io, L, IO->done, fill_ticks, clear_nstep, workspace, workspace_bytes);
+  rc = fill_ws_args(a, P, S, &io, L, fill_ticks, clear_nstep, workspace, workspace_bytes);
+  if (rc) return rc;
+  rc = step_impl(P, R, S, IO, L, a.count, a.list);  // the step kernel appends the finished envs to the list
+  if (rc) return rc;
+  return launch_fill(a, L->n_envs);
 }
 
 extern "C" int mdg_init_state(const MdgParams* P, const MdgReward* R, const MdgState* S, const MdgLaunch* L) {
@@ -556,8 +529,8 @@ extern "C" int mdg_init_state(const MdgParams* P, const MdgReward* R, const MdgS
   a.P = *P;
   if (R) a.R = *R; else { memset(&a.R, 0, sizeof(a.R)); a.R.nstep = 1; }
   a.S = *S; a.L = *L;
-  const unsigned grid = (unsigned)((L->n_envs + kBlock - 1) / kBlock);
-  init_kernel<<<grid, kBlock, 0, (cudaStream_t)L->stream>>>(a);
+  const unsigned grid = (unsigned)((L->n_envs + 128 - 1) / 128);
+  init_kernel<<<grid, 128, 0, (cudaStream_t)L->stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_init_state launch");
 }
 
@@ -568,8 +541,8 @@ extern "C" int mdg_refresh_folds(const MdgParams* P, const MdgState* S, const Md
   if (L->n_envs == 0) return MDG_OK;
   FoldArgs a;
   a.P = *P; a.S = *S; a.N = L->n_envs;
-  const unsigned grid = (unsigned)((L->n_envs + kBlock - 1) / kBlock);
-  refresh_folds_kernel<<<grid, kBlock, 0, (cudaStream_t)L->stream>>>(a);
+  const unsigned grid = (unsigned)((L->n_envs + 128 - 1) / 128);
+  refresh_folds_kernel<<<grid, 128, 0, (cudaStream_t)L->stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_refresh_folds launch");
 }
 
@@ -587,6 +560,7 @@ extern "C" int mdg_sizeof(int which) {
     case 7: return (int)sizeof(MdgWindow);
     case 8: return (int)sizeof(MdgReplay);
     case 9: return (int)sizeof(MdgReplayBatch);
+    case 10: return (int)sizeof(MdgRewardNorm);
   }
   return -1;
 }

@@ -82,7 +82,8 @@ def _reset_workspace(lib_, P, n_envs, fill_ticks, device, stream_ptr=None):
     key = (device.index, _raw_stream(device.index) if stream_ptr is None else stream_ptr)
     ws = _RESET_WS.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        # the 256-byte header {list length, exit ticket} must be zero before the first use; the kernels leave it zero
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
         _RESET_WS[key] = ws
     return ws
 
@@ -131,6 +132,7 @@ class Env:
         self._version = 0
         self._derived_version = -1
         self.launches = 0  # kernels launched so far (bench.py's gpu_launches)
+        self.flags = 0     # MdgLaunch.flags (validation: A.FLAG_FORCE_EXACT_GATE)
         with torch.cuda.device(self.device):
             check(self._lib.mdg_init_state(C.byref(self.P), C.byref(self.R), C.byref(self._S), C.byref(self._launch())))
             self.launches += 1
@@ -195,6 +197,7 @@ class Env:
         L.seed = self.seed
         L.env_offset = self.env_offset
         L.stream = self._stream_ptr if self._stream_ptr is not None else _raw_stream(self.device.index)
+        L.flags = self.flags
         return L
 
     def bind_stream(self, stream):
@@ -261,8 +264,7 @@ class Env:
         check(self._lib.mdg_reset_ws(C.byref(self.P), C.byref(self._S), C.byref(io), C.byref(self._launch()),
                                      None if m is None else m.data_ptr(), int(fill_ticks), int(clear_nstep),
                                      ws.data_ptr(), ws.numel()))
-        # scan + (rng, recur) per pass of at most 65,536 listed envs
-        self.launches += 1 + 2 * max(1, -(-self.N // 65536))
+        self.launches += 2  # list scan + refill kernel
         self._version += 1
         del keep
 
@@ -334,7 +336,7 @@ class Env:
                 ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr)
                 check(self._lib.mdg_step_autoreset(self._pP, self._pR, self._pS, self._pIO, self._pL, self.k, 1,
                                                    ws.data_ptr(), ws.numel()))
-                self.launches += 2 + 2 * max(1, -(-self.N // 65536))
+                self.launches += 2  # step kernel (appends the finished envs to the list) + refill kernel
                 auto_reset = False
             else:
                 check(self._lib.mdg_step(self._pP, self._pR, self._pS, self._pIO, self._pL))
@@ -384,7 +386,7 @@ class Env:
                     ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr)
                     check(self._lib.mdg_step_autoreset(self._pP, self._pR, self._pS, self._pIO, self._pL, self.k, 1,
                                                        ws.data_ptr(), ws.numel()))
-                    self.launches += 1 + 2 * max(1, -(-self.N // 65536))
+                    self.launches += 1  # + the refill kernel
                     auto_reset = False
                 else:
                     check(self._lib.mdg_step(self._pP, self._pR, self._pS, self._pIO, self._pL))

@@ -43,7 +43,7 @@ class OrcStepOut(C.Structure):
 def build(force=False):
     """Compile oracle/libmdg_oracle.so (gcc, -ffp-contract=off)."""
     so = os.path.join(_HERE, "libmdg_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("mdg_oracle.c", "mdg_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("mdg_oracle.c", "mdg_oracle.h", "reward_norm_oracle.c")]
     src.append(os.path.join(_HERE, "..", "include", "madigan_b200.h"))
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.run(["make", "-s", "-C", _HERE], check=True, capture_output=True)
@@ -104,6 +104,10 @@ def lib():
         L.orc_batch_reset.restype = None
         L.orc_batch_derived.argtypes = [C.c_void_p, C.POINTER(A.MdgDerived)]
         L.orc_batch_derived.restype = None
+        L.orc_reward_norm_reset.argtypes = [C.POINTER(A.MdgRewardNorm), C.c_void_p]
+        L.orc_reward_norm_reset.restype = None
+        L.orc_reward_norm_stream.argtypes = [C.POINTER(A.MdgRewardNorm), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_reward_norm_stream.restype = None
         _LIB = L
     return _LIB
 
@@ -375,3 +379,33 @@ class OracleBatch:
         nv = self.n_valid if n_valid is None else n_valid
         idx = [(self.head - (nv - 1 - s)) % self.k for s in range(nv)]
         return np.ascontiguousarray(self.obs_price[idx].transpose(2, 0, 1))
+
+
+class OracleRewardNorm:
+    """N streaming reward normalisers (reward_normalization.pyx) on numpy state laid out like the CUDA path's."""
+    KINDS = {"NullShaper": A.RN_NULL, "SharpeFixedWindow": A.RN_SHARPE_FIXED, "SortinoFixedWindowA": A.RN_SORTINO_A,
+             "SortinoFixedWindowB": A.RN_SORTINO_B, "SortinoFixedWindowC": A.RN_SORTINO_C,
+             "SharpeEWMA": A.RN_SHARPE_EWMA}
+
+    def __init__(self, kind, n_envs, window=2):
+        self.L = lib()
+        self.N = int(n_envs)
+        w = max(int(window), 1)
+        self.state = dict(buffer=np.zeros((w, self.N)), size=np.zeros(self.N, np.int32), front=np.zeros(self.N, np.int32),
+                          count=np.zeros(self.N, np.int32), mean_est=np.zeros(self.N), ssq=np.zeros(self.N),
+                          ewma=np.zeros(self.N), ewma_old=np.zeros(self.N), ewssq_old=np.zeros(self.N),
+                          ewssq=np.zeros(self.N), w1=np.ones(self.N), w2=np.ones(self.N))
+        self.rn = A.MdgRewardNorm(kind=self.KINDS[kind], window=w, n_envs=self.N, alpha=2 / (float(w + 1)))
+        for k_, v in self.state.items():
+            setattr(self.rn, k_, _ptr(v))
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.L.orc_reward_norm_reset(C.byref(self.rn), _ptr(m))
+
+    def stream(self, reward, reset_mask=None):
+        r = np.ascontiguousarray(reward, dtype=np.float64)
+        m = None if reset_mask is None else np.ascontiguousarray(reset_mask, dtype=np.uint8)
+        out = np.zeros(self.N)
+        self.L.orc_reward_norm_stream(C.byref(self.rn), _ptr(r), _ptr(m), _ptr(out))
+        return out
