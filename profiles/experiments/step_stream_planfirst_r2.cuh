@@ -1,13 +1,23 @@
-// Fused Env.step / Env.reset kernels for N independent environments (sm_100a).
+// Fused Env.step kernel for N independent environments (sm_100a).
 //
-// One thread per env STREAMS over its assets in a rolled loop: state tensors are
-// [rows][N], so every load/store is one coalesced 256-byte run per warp, each value is
-// read once, and the kernel is a few thousand instructions (an earlier fully unrolled,
-// register-resident version was I-cache bound, profiles/r1_notes.md).  One launch does what the
-// reference does across Env.h:189-256, Broker.cpp:124-178, Portfolio.cpp:140-323,
+// One launch does what the reference does across Env.h:189-256, Broker.cpp:124-178, Portfolio.cpp:140-323,
 // the DataSource.cpp getData family, offpolicy_q.py:140-164 and nstep_buffer.py:
-//   transact (sequential over assets, risk-gated) -> generator tick -> equity,
-//   reward, done -> newest observation-ring row -> agent reward -> shaped reward.
+//   transact (sequential over assets, risk-gated) -> generator tick -> equity, reward, done ->
+//   newest observation-ring row -> agent reward -> shaped reward -> (auto-reset) done list.
+//
+// One thread per env STREAMS over its assets (one OU pair per iteration in the headline specialisation); state
+// tensors are [rows][N], so every load/store of a warp is one contiguous 256-byte run and every value is read once.
+// A 65,536-env launch is one wave of 13.8 warps per SM: what bounds it is the length of one thread's dependent
+// instruction chain, so the body of an iteration is organised for instruction-level parallelism:
+//   PLAN   both orders of the pair first -- the outcome Broker::handleTransaction would produce if its risk gate
+//          says green, and what it would add to the running sums: independent of the trades of earlier assets, so
+//          the two plans (each ~100 fp64 instructions with a division) interleave;
+//   GATE   then the only inherently sequential part (cash and the gate of asset i see the trades of assets < i,
+//          Broker.cpp:144-158): a branch-free decision from running sums, a handful of dependent instructions per
+//          asset, and the selection of the planned or the old ledger values;
+//   TICK   then the generator tick, the stores, the folds.
+// (Round 2 also measured a tile design -- 8 warps per 32 envs plus a chain warp, plans through shared memory --
+// profiles/experiments/step_tile_phased_r2.cuh: 64 us per 65,536-env launch against 41 us for this layout.)
 // HBM-bound integer/fp64 work: no tensor cores.
 #pragma once
 #include <math.h>
@@ -23,12 +33,20 @@ struct StepArgs {
   MdgState S;
   MdgStepIO IO;
   MdgLaunch L;
-  int units_v2;     // set by launch_step: the units matrix can be read with 16-byte loads (aligned base, even nA)
   int* done_count;  // nullable (auto-reset): number of envs that finished this step ...
   int* done_list;   // ... and their indices, appended warp by warp in the kernel's tail
 };
 
-constexpr int kBlock = 128;
+#ifndef MDG_BLOCK
+#define MDG_BLOCK 128
+#endif
+#ifndef MDG_MINB_SMALL
+#define MDG_MINB_SMALL 4   // blocks per SM of the one-wave variant (register cap = 65,536 / (MDG_BLOCK * MDG_MINB_SMALL))
+#endif
+#ifndef MDG_MINB_LARGE
+#define MDG_MINB_LARGE 3
+#endif
+constexpr int kBlock = MDG_BLOCK;
 
 // experiment knobs (MDG_EXTRA_NVCC_FLAGS + MDG_LIB_VARIANT, see build.py); the defaults are the measured best
 #ifndef MDG_PFDIST
@@ -40,20 +58,7 @@ constexpr int kBlock = 128;
 #ifndef MDG_TAIL_UNROLL
 #define MDG_TAIL_UNROLL 2
 #endif
-#ifndef MDG_UNITS_CG
-#define MDG_UNITS_CG 0  // 1: units read as 16-byte vectors that bypass L1 (measured slower at 65,536 envs)
-#endif
-#ifndef MDG_ST
-#define MDG_ST 0        // 0: plain stores, 1: st.global.cg (no L1 allocation) for state and outputs
-#endif
-#ifndef MDG_AB_L1
-#define MDG_AB_L1 0
-#endif
 constexpr int kRngUnroll = MDG_RNG_UNROLL, kTailUnroll = MDG_TAIL_UNROLL;  // #pragma unroll does not expand macros
-
-template <class T> __device__ __forceinline__ void gst(T* p, T v) {
-  if (MDG_ST) __stcg(p, v); else *p = v;
-}
 
 // ---------------------------------------------------------------------------
 // reward shapers (utils/buffers/nstep_buffer.py), one scalar component
@@ -183,9 +188,10 @@ static __device__ __noinline__ double shaper_pop(const MdgReward& R, const NStep
 }
 
 // ReplayBuffer.add (replay_buffer.py:68-80) + NStepBuffer.pop_nstep_sarsd (nstep_buffer.py:342-361)
-// for component c of env e: add `raw`, pop once when full, drain on done.
-static __device__ __noinline__ void shaper_add(const StepArgs& a, int64_t e, int c, int ra, double raw, bool done,
-                                           int len_before, int& len_after, int& n_popped) {
+// for component c of env e: add `raw`, pop once when full, drain on done.  `valid` gates every store (lanes
+// past the end of the slab run on a clamped env index).
+static __device__ __noinline__ void shaper_add(const StepArgs& a, int64_t e, bool valid, int c, int ra, double raw,
+                                               bool done, int len_before, int& len_after, int& n_popped) {
   const MdgReward& R = a.R;
   const int64_t N = a.L.n_envs;
   const int n = R.nstep;
@@ -203,20 +209,22 @@ static __device__ __noinline__ void shaper_add(const StepArgs& a, int64_t e, int
   int base = a.L.nstep_pos - len_before;
   if (base < 0) base += n;
   v.base = base;
-  if (n > 1) a.S.nstep_ring[((int64_t)a.L.nstep_pos * ra + c) * N + e] = raw;
+  if (n > 1 && valid) a.S.nstep_ring[((int64_t)a.L.nstep_pos * ra + c) * N + e] = raw;
   int first = 0, k = 0;
   if (v.len >= n) {
-    a.IO.shaped_reward[((int64_t)k * ra + c) * N + e] = shaper_pop(R, v, first, A, B);
+    const double s = shaper_pop(R, v, first, A, B);
+    if (valid) a.IO.shaped_reward[((int64_t)k * ra + c) * N + e] = s;
     ++first; ++k;
   }
   if (done) {
 #pragma unroll 1
     while (first < v.len) {
-      a.IO.shaped_reward[((int64_t)k * ra + c) * N + e] = shaper_pop(R, v, first, A, B);
+      const double s = shaper_pop(R, v, first, A, B);
+      if (valid) a.IO.shaped_reward[((int64_t)k * ra + c) * N + e] = s;
       ++first; ++k;
     }
   }
-  if (moments) {
+  if (moments && valid) {
     a.S.shaper_A[(int64_t)c * N + e] = A;
     a.S.shaper_B[(int64_t)c * N + e] = B;
   }
@@ -225,7 +233,7 @@ static __device__ __noinline__ void shaper_add(const StepArgs& a, int64_t e, int
 }
 
 // ---------------------------------------------------------------------------
-// the step kernel
+// the ledger
 // ---------------------------------------------------------------------------
 // rows of MdgState.folds
 #define MDG_FOLD_AV 0
@@ -234,10 +242,111 @@ static __device__ __noinline__ void shaper_add(const StepArgs& a, int64_t e, int
 #define MDG_FOLD_SE 3
 #define MDG_FOLD_G 4
 
+struct StepConsts {
+  double reqM, maintM, band_scale;
+  double g1, g2;  // magnitude-bound coefficients of one transaction
+  bool reqM_ok;
+  bool force_exact;  // MdgLaunch.flags & MDG_FLAG_FORCE_EXACT_GATE: every gate takes the exact (cold) path
+};
+
+__device__ __forceinline__ StepConsts make_consts(const StepArgs& a) {
+  const MdgParams& P = a.P;
+  StepConsts c;
+  c.reqM = P.required_margin;
+  c.maintM = P.maintenance_margin;
+  c.reqM_ok = c.reqM > 0. && c.reqM <= 1e6;
+  c.band_scale = 1e-9 * (1. + fabs(c.maintM)) * (c.reqM > 1. ? c.reqM : 1.);
+  c.g1 = 6. + 3. * fabs(P.slippage_rel) + fabs(P.tcost_rel);
+  c.g2 = 3. * fabs(P.slippage_abs);
+  c.force_exact = (a.L.flags & MDG_FLAG_FORCE_EXACT_GATE) != 0;
+  return c;
+}
+
+// One order, everything that does NOT depend on the trades of earlier assets: the outcome
+// Broker::handleTransaction would produce if the risk gate says green (Broker.cpp:124-142,171-178;
+// Portfolio.cpp:284-323, same operations in the same order), the three cash updates of that outcome, and the
+// deltas it would add to the decision sums of the gate chain.
+enum { PF_NZ = 1, PF_GATED = 2, PF_OPP = 4, PF_F1 = 8, PF_F3 = 16 };
+struct Plan {
+  double amtR;              // |price * (units [+ ledger])| * requiredMargin: what the gate compares with balance + pnl
+  double dX, dBAL, dE, dG;  // deltas of the decision sums
+  double c1, c2, c3;        // cash += c1 (reversal through zero), cash -= c2 (margin + cost), cash -= c3 (margin returned)
+  double ncur, nmep, nbm;   // ledger, mean entry price, borrowed margin after the order
+  unsigned flags;           // PF_*
+};
+
+// Broker::applySlippage / getTransactionCost  Broker.cpp:171-178
+__device__ __forceinline__ void order_price_cost(const MdgParams& P, double price, double units, double& tp,
+                                                 double& tc) {
+  const double slippage = (price * P.slippage_rel) + P.slippage_abs;
+  tp = units < 0 ? (price - slippage) : (price + slippage);
+  tc = fabs(units * price) * P.tcost_rel + P.tcost_abs;
+}
+
+__device__ __forceinline__ void plan_order(const MdgParams& P, const StepConsts& c, double price, double cur,
+                                           double mep, double bm, double units, Plan& o) {
+  const double units_req = units;
+  const bool nz = units != 0.;  // Broker.cpp:126 (NaN units do enter, as in the reference)
+  const bool opposite = (signbit(units) != 0) != (signbit(cur) != 0);
+  const bool gated = nz && (!opposite || units > -1 * cur);  // Portfolio.cpp:257-258: only these orders are gated
+  o.amtR = fabs(price * (opposite ? units + cur : units)) * c.reqM;
+  double transactionPrice, transactionCost;
+  order_price_cost(P, price, units, transactionPrice, transactionCost);
+  // Portfolio::handleTransaction  Portfolio.cpp:284-323
+  const double prev_val = cur * price;
+  const double o_ml = mep * cur, o_bm = bm;
+  const double o_se = (cur < 0.) ? o_ml : 0.;
+  double c1 = 0., c3 = 0.;
+  bool f1 = false, f3 = false;
+  if (opposite) {
+    if (fabs(units) > fabs(cur)) {
+      units += cur;
+      f1 = true; c1 = cur * transactionPrice;
+      cur = 0.;
+      mep = transactionPrice;
+    }
+  } else if (nz) {  // (a zero order on a flat position would divide 0 by 0; it never executes)
+    mep += (transactionPrice - mep) * (units / (units + cur));
+  }
+  const double amount = transactionPrice * units;
+  const double marginToUse = amount * c.reqM;
+  const double marginToBorrow = amount - marginToUse;
+  bm += marginToBorrow;
+  const double c2 = marginToUse + transactionCost;
+  cur += units;
+  if (fabs(cur) < 0.000001) {
+    mep = 0.;
+    if (bm > 0.) { f3 = true; c3 = bm; bm = 0.; }
+  }
+  if (bm < 0.) { f3 = true; c3 = bm; bm = 0.; }
+  o.c1 = c1; o.c2 = c2; o.c3 = c3;
+  o.ncur = cur; o.nmep = mep; o.nbm = bm;
+  // deltas of the decision sums (any rounding is fine here: the gate trusts them only outside a 1e-9*G band)
+  const double n_av = cur * price, n_ml = mep * cur;
+  const double dAV = n_av - prev_val, dML = n_ml - o_ml, dBM = bm - o_bm;
+  const double dSE = ((cur < 0.) ? n_ml : 0.) - o_se;
+  const double dCash = (c1 - c2) - c3;
+  o.dBAL = dCash + dSE;
+  o.dX = o.dBAL + (dAV - dML);
+  o.dE = (dCash + dAV) - dBM;
+  // every new term's magnitude is at most its old magnitude (already in G) plus |units|*(|price|+|tp|), three
+  // terms, plus the cost; with |tp| <= |price|(1+|slip_rel|)+|slip_abs| and |cost| <= |units price||tc_rel|+|tc_abs|
+  // that is |units| * (|price| * g1 + g2) (+ |tc_abs|, added once per asset at the start of the chain)
+  o.dG = fabs(units_req) * (fabs(price) * c.g1 + c.g2);
+  o.flags = (nz ? PF_NZ : 0) | (gated ? PF_GATED : 0) | (opposite ? PF_OPP : 0) | (f1 ? PF_F1 : 0) | (f3 ? PF_F3 : 0);
+}
+
+// dqn.py:165-178: centred action times (unit_size * availableMargin / price); action 0 closes an open position
+__device__ __forceinline__ double action_units(int act, int half, double scale, double price, double cur) {
+  if (act == 0) return (cur != 0.) ? -cur : 0.;
+  return (double)(act - half) * (scale / price);
+}
+
+
 // Exact risk gate of asset i (Portfolio::checkRisk(i, units), Portfolio.cpp:254-279): every accounting
 // quantity is a left-to-right fold over the assets, exactly as in the oracle.  COLD path, called only when
-// the cheap bound in step_kernel cannot decide.  (pav..pse) are the folds over the already processed
-// assets 0..i-1 (final values); assets i.. are untouched so far and are re-read from global memory.
+// the cheap bound cannot decide.  (av..se) are the folds over the already processed assets 0..i-1 (final values);
+// assets i.. are untouched so far and are re-read from global memory.
 static __device__ __noinline__ int exact_gate(const MdgState& S, int64_t N, int64_t e, int na, double cash,
                                               double reqM, double maintM, int i, double units, double av,
                                               double ml, double bms, double se) {
@@ -264,112 +373,67 @@ static __device__ __noinline__ int exact_gate(const MdgState& S, int64_t N, int6
   return MDG_RISK_GREEN;
 }
 
-// Registers of one env while it streams over its assets
+// Registers of one env while it streams over its assets.
+// DECISION sums (approximate, updated by one precomputed delta per accepted order -- the gates' critical path):
+//   X = balance + pnl (= availableMargin * requiredMargin), BAL = balance, E = equity at the old prices,
+//   G = bound on the sum of the magnitudes of everything that went into them.
+// EXACT values (the reference's own operation order): cash with every Portfolio::handleTransaction update applied
+// in sequence, and the left-to-right folds of the final ledger.
 struct StepAcc {
   double cash;
-  double rAV, rML, rBM, rSE, G;  // running sums (cheap risk bound) and their magnitude bound
-  double pav, pml, pbm, pse;     // exact left-to-right folds over the processed assets, old prices
-  double nav, gsum;              // exact fold of ledger*new price; magnitude sum for the next step
-  double rprod, inv_prev;        // reduced agent reward accumulated in the asset loop (post_tick)
+  double X, BAL, E, G;
+  double pav, pml, pbm, pse;  // exact left-to-right folds over the processed assets, old prices
+  double nav, gsum;           // exact fold of ledger*new price; magnitude sum for the next step
+  double rprod, inv_prev;     // reduced agent reward accumulated in the asset loop (post_tick)
   bool reduce_inloop;
   bool bad_risk;
 };
 
-struct StepConsts {
-  double reqM, maintM, band_scale;
-  double g1, g2;  // magnitude-bound coefficients of one transaction (tx_asset)
-  bool reqM_ok;
-  bool force_exact;  // MdgLaunch.flags & MDG_FLAG_FORCE_EXACT_GATE: every gate takes the exact (cold) path
-};
-
-// Broker::handleTransaction(port, i, units) (Broker.cpp:124-142) for one asset whose state is in registers:
-// risk gate (Portfolio.cpp:254-279), slippage/cost (Broker.cpp:171-178), ledger update (Portfolio.cpp:284-323).
-//
-// The gate compares folds over the whole portfolio with thresholds.  Recomputing the folds per asset is
-// O(nA^2) fp64 work, so the gate first uses RUNNING sums (O(1) update per transaction, hence rounded
-// differently from a fresh fold) with a rigorous bound: running and exact folds differ by < 1e-13 * G
-// (G = sum of magnitudes); a decision is taken from the running sums only when it clears its threshold by
-// 1e-9 * G.  Otherwise -- a knife-edge, NaN/Inf, a non-positive required margin -- the exact left-to-right
-// folds decide (exact_gate).  Decisions, and therefore ledgers, are bit-identical to the oracle's either way.
-__device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c, StepAcc& A, int64_t N, int64_t e,
-                                         int na, int i, double price, double& cur, double& mep, double& bm,
-                                         double units, double& tp, double& tu, double& tc, int& risk,
-                                         double& prev_val) {
-  const MdgParams& P = a.P;
+// Broker::handleTransaction(port, i, units) (Broker.cpp:124-142) of a PLANNED order: the risk gate
+// (Portfolio::checkRisk(i, units), Portfolio.cpp:254-279) on the decision sums, then the planned outcome or none.
+// The gate compares folds over the whole portfolio with thresholds; the decision sums are rounded differently
+// from the reference's fresh left-to-right folds (they differ by < 1e-13 * G), so a decision is taken from them
+// only when it clears its threshold by 1e-9 * G: `certain`.  Otherwise -- a knife-edge, NaN/Inf, a non-positive
+// required margin -- the exact folds decide (exact_gate, cold).  Decisions, and therefore ledgers, are
+// bit-identical to the oracle's either way.
+__device__ __forceinline__ void gate_apply(const StepArgs& a, const StepConsts& c, StepAcc& A, const Plan& o, int64_t N,
+                                           int64_t e, int na, int i, double price, double& cur, double& mep,
+                                           double& bm, double units, double& tp, double& tu, double& tc) {
   const MdgState& S = a.S;
-  prev_val = cur * price;  // offpolicy_q.py:141
+  const bool nz = (o.flags & PF_NZ) != 0, gated = (o.flags & PF_GATED) != 0, opp = (o.flags & PF_OPP) != 0;
+  // (the order's own magnitude |amount| is at most dG / 6, so G + dG bounds G + |amount|)
+  const double nG = A.G + o.dG;
+  const double band = c.band_scale * nG;
+  const double d1 = A.X - o.amtR;               // availableMargin <= |amount|  <=>  d1 <= 0
+  const double m = c.maintM * (A.X - A.BAL);    // Portfolio::checkRisk() first (:268), :243-252
+  const double d3 = A.E + m, d4 = A.X + m;
+  const bool ok1 = (fabs(d1) > band) & (fabs(A.BAL) > band);
+  const bool ok2 = (fabs(d3) > band) & (fabs(d4) > band);
+  const bool certain = c.reqM_ok & ok1 & (opp | ok2) & !c.force_exact;
+  const bool insuff = (d1 <= 0.) | (A.BAL <= 0.);
+  const bool mcall = !opp & ((d3 <= 0.) | (d4 <= 0.));
+  int risk = (gated & (insuff | mcall)) ? (mcall ? MDG_RISK_MARGIN_CALL : MDG_RISK_INSUFF_MARGIN) : MDG_RISK_GREEN;
+  if (gated & !certain)
+    risk = exact_gate(S, N, e, na, A.cash, c.reqM, c.maintM, i, units, A.pav, A.pml, A.pbm, A.pse);
   tp = 0.; tu = 0.; tc = 0.;
-  risk = MDG_RISK_GREEN;
-  if (units != 0.) {  // Broker.cpp:126 (NaN units do enter, as in the reference)
-    const bool opposite = (signbit(units) != 0) != (signbit(cur) != 0);
-    if (!opposite || units > -1 * cur) {  // Portfolio.cpp:257-258: only these orders are gated
-      const double amt = fabs(price * (opposite ? units + cur : units));
-      const double bal = A.cash + A.rSE, pnl = A.rAV - A.rML, x = bal + pnl;
-      const double band = c.band_scale * (A.G + amt);
-      const double d1 = x - amt * c.reqM;  // availableMargin <= |amount|  <=>  d1 <= 0
-      bool certain = c.reqM_ok && fabs(d1) > band && fabs(bal) > band;
-      int r_fast = (d1 <= 0. || bal <= 0.) ? MDG_RISK_INSUFF_MARGIN : MDG_RISK_GREEN;
-      if (!opposite) {  // Portfolio::checkRisk() first (:268), :243-252
-        const double m = c.maintM * pnl;
-        const double d3 = (A.cash + A.rAV - A.rBM) + m, d4 = x + m;
-        certain = certain && fabs(d3) > band && fabs(d4) > band;
-        if (d3 <= 0. || d4 <= 0.) r_fast = MDG_RISK_MARGIN_CALL;
-      }
-      risk = (certain && !c.force_exact)
-                 ? r_fast
-                 : exact_gate(S, N, e, na, A.cash, c.reqM, c.maintM, i, units, A.pav, A.pml, A.pbm, A.pse);
-    }
-    if (risk == MDG_RISK_GREEN) {
-      // Broker::applySlippage / getTransactionCost  Broker.cpp:171-178
-      const double slippage = (price * P.slippage_rel) + P.slippage_abs;
-      const double transactionPrice = units < 0 ? (price - slippage) : (price + slippage);
-      const double transactionCost = fabs(units * price) * P.tcost_rel + P.tcost_abs;
-      tp = transactionPrice; tu = units; tc = transactionCost;
-      // Portfolio::handleTransaction  Portfolio.cpp:284-323
-      const double o_ml = mep * cur, o_bm = bm;
-      const double o_se = (cur < 0.) ? o_ml : 0.;
-      if (opposite) {
-        if (fabs(units) > fabs(cur)) {
-          units += cur;
-          A.cash += cur * transactionPrice;
-          cur = 0.;
-          mep = transactionPrice;
-        }
-      } else {
-        mep += (transactionPrice - mep) * (units / (units + cur));
-      }
-      const double amount = transactionPrice * units;
-      const double marginToUse = amount * c.reqM;
-      const double marginToBorrow = amount - marginToUse;
-      bm += marginToBorrow;
-      A.cash -= (marginToUse + transactionCost);
-      cur += units;
-      if (fabs(cur) < 0.000001) {
-        mep = 0.;
-        if (bm > 0.) { A.cash -= bm; bm = 0.; }
-      }
-      if (bm < 0.) { A.cash -= bm; bm = 0.; }
-      gst(&S.ledger[(int64_t)i * N + e], cur);
-      gst(&S.mean_entry[(int64_t)i * N + e], mep);
-      gst(&S.borrowed[(int64_t)i * N + e], bm);
-      // running sums and their magnitude bound
-      const double n_av = cur * price, n_ml = mep * cur;
-      A.rAV += n_av - prev_val;
-      A.rML += n_ml - o_ml;
-      A.rBM += bm - o_bm;
-      A.rSE += ((cur < 0.) ? n_ml : 0.) - o_se;
-      // every new term's magnitude is at most its old magnitude (already in G) plus |units|*(|price|+|tp|), three
-      // terms, plus the cost; with |tp| <= |price|(1+|slip_rel|)+|slip_abs| and |cost| <= |units price||tc_rel|+|tc_abs|
-      // that is |units| * (|price| * g1 + g2) (+ |tc_abs|, added once per asset in the prologue)
-      A.G += fabs(tu) * (fabs(price) * c.g1 + c.g2);
-    } else if (risk != MDG_RISK_INSUFF_MARGIN) {
-      A.bad_risk = true;
-    }
+  if (nz & (risk == MDG_RISK_GREEN)) {
+    order_price_cost(a.P, price, units, tp, tc);  // (the same expressions as in plan_order)
+    tu = units;
+    A.X += o.dX; A.BAL += o.dBAL; A.E += o.dE; A.G = nG;
+    if (o.flags & PF_F1) A.cash += o.c1;  // Portfolio.cpp:296
+    A.cash -= o.c2;                       // :311
+    if (o.flags & PF_F3) A.cash -= o.c3;  // :316-321
+    cur = o.ncur; mep = o.nmep; bm = o.nbm;
+    S.ledger[(int64_t)i * N + e] = cur;
+    S.mean_entry[(int64_t)i * N + e] = mep;
+    S.borrowed[(int64_t)i * N + e] = bm;
+  } else if (nz & (risk != MDG_RISK_INSUFF_MARGIN)) {
+    A.bad_risk = true;
   }
   if (a.L.mode != MDG_MODE_HOLD) {
-    gst(&a.IO.trans_price[(int64_t)i * N + e], tp);
-    gst(&a.IO.trans_units[(int64_t)i * N + e], tu);
-    gst(&a.IO.trans_cost[(int64_t)i * N + e], tc);
+    a.IO.trans_price[(int64_t)i * N + e] = tp;
+    a.IO.trans_units[(int64_t)i * N + e] = tu;
+    a.IO.trans_cost[(int64_t)i * N + e] = tc;
     a.IO.risk[(int64_t)i * N + e] = (uint8_t)risk;
   }
   // exact folds of the final ledger, old prices (Portfolio.cpp:180-197,207-209)
@@ -391,19 +455,13 @@ template <bool PAIRS> __device__ __forceinline__ int stash_pm_row(int j, int na)
   return PAIRS ? 4 * (j >> 1) + 2 + (j & 1) : na + j;
 }
 
-// dqn.py:165-178: centred action times (unit_size * availableMargin / price); action 0 closes an open position
-__device__ __forceinline__ double action_units(int act, int half, double scale, double price, double cur) {
-  if (act == 0) return (cur != 0.) ? -cur : 0.;
-  return (double)(act - half) * (scale / price);
-}
-
 // after the tick of asset i: state/observation stores, fold of the new position value, reward stash
 template <bool PAIRS, int BS>
 __device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t N, int64_t e, int na, int i,
                                           double cur, double newp, double prev_val, double tp, double tu,
                                           double tc, double* st) {
-  gst(&a.S.price[(int64_t)i * N + e], newp);
-  gst(&a.IO.obs_price[((int64_t)a.L.head * na + i) * N + e], newp);  // State.price row (Env.h:202,228,254)
+  a.S.price[(int64_t)i * N + e] = newp;
+  a.IO.obs_price[((int64_t)a.L.head * na + i) * N + e] = newp;  // State.price row (Env.h:202,228,254)
   const double cur_val = cur * newp;
   A.nav = (i == 0) ? cur_val : A.nav + cur_val;
   A.gsum += fabs(cur_val);
@@ -451,7 +509,6 @@ __device__ __forceinline__ int gen_state_rows(const MdgAssetGen& g) {
 //   128 registers -> 4 blocks of 128 per SM: the 443 envs per SM of a 65,536-env launch are resident in ONE
 //     wave (that launch is latency-bound: a second wave would cost as much as the first);
 //   168 registers -> 3 blocks per SM, no spills: best throughput when there are many waves (>= 262,144 envs).
-// (64-thread blocks x 7 per SM at 144 registers were measured slower than either.)
 template <bool PAIRS, int BS, bool ACTIONS>
 __device__ __forceinline__ void step_body(const StepArgs& a) {
   // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff (and, in the
@@ -465,11 +522,9 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   const int64_t e = (int64_t)blockIdx.x * BS + tid;
   const int mode = a.L.mode;
   double* st = stash + tid;  // this thread's column, [row * BS]
-  // the caller's units matrix is (N, nA) env-major: a thread's row is one 128-byte line.  Read as 16-byte
-  // vectors (one per pair) that bypass L1, so that the 64 KB of unit lines per SM do not evict the prefetched state
-  const bool units_v2 = MDG_UNITS_CG && PAIRS && mode == MDG_MODE_MULTI && a.units_v2;
   if (e >= N) return;
   const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
+  const bool cosine = shaping && a.R.shaper == MDG_SHAPER_COSINE;
   const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;  // unused with actions
   const bool moments = shaping && (a.R.shaper == MDG_SHAPER_DSR || a.R.shaper == MDG_SHAPER_DDR);
   auto prefetch_hint = [&](int pp) {
@@ -484,6 +539,11 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.borrowed + o1));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e));
   };
+  // the reduced reward's n-step shaper with nstep == 1 (add, pop at once) runs inline in the tail; its moments are
+  // loaded here, at the start
+  const bool reduce_plain = shaping && a.R.reduce_rewards && !cosine;
+  const bool inline_shaper = reduce_plain && a.R.nstep == 1 && (moments || a.R.shaper == MDG_SHAPER_SUM);
+  double shA = 0., shB = 0.;
   if (PAIRS) {
     // The next pair's lines are pulled into L1 with prefetch hints and loaded when needed.  (Holding the next
     // pair in registers instead made the compiler spill it at the 128-register budget -- a local store right
@@ -493,11 +553,6 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
     if (MDG_PFDIST > 1 && na > 2) prefetch_hint(1);
     if (mode == MDG_MODE_MULTI && urow) asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
   }
-  // The reduced reward's n-step shaper with nstep == 1 (add, pop at once: the common case) runs inline in the tail;
-  // its moments are loaded here, at the start, so that no load latency is left at the end of the thread's chain.
-  const bool inline_shaper = shaping && a.R.reduce_rewards && a.R.shaper != MDG_SHAPER_COSINE && a.R.nstep == 1 &&
-                             (moments || a.R.shaper == MDG_SHAPER_SUM);
-  double shA = 0., shB = 0.;
   if (moments && inline_shaper) {
     shA = a.S.shaper_A[e];
     shB = a.S.shaper_B[e];
@@ -512,45 +567,38 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   // Folds of the incoming portfolio.  They are exactly the folds this kernel (or reset/init/refresh)
   // computed at the end of the previous call -- same values, same left-to-right order -- so they are
   // carried in state instead of re-reading the whole portfolio before the first transaction.
-  A.rAV = S.folds[(int64_t)MDG_FOLD_AV * N + e];
-  A.rML = S.folds[(int64_t)MDG_FOLD_ML * N + e];
-  A.rBM = S.folds[(int64_t)MDG_FOLD_BM * N + e];
-  A.rSE = S.folds[(int64_t)MDG_FOLD_SE * N + e];
-  A.G = S.folds[(int64_t)MDG_FOLD_G * N + e];
+  {
+    const double rAV = S.folds[(int64_t)MDG_FOLD_AV * N + e], rML = S.folds[(int64_t)MDG_FOLD_ML * N + e];
+    const double rBM = S.folds[(int64_t)MDG_FOLD_BM * N + e], rSE = S.folds[(int64_t)MDG_FOLD_SE * N + e];
+    A.G = S.folds[(int64_t)MDG_FOLD_G * N + e] + na * fabs(P.tcost_abs);  // + the absolute cost of up to nA transactions
+    A.BAL = A.cash + rSE;          // Portfolio.cpp:192-197
+    A.X = A.BAL + (rAV - rML);     // availableMargin * requiredMargin, :184-186, :229-231
+    A.E = A.cash + rAV - rBM;      // equity, :211-213
+  }
   A.pav = A.pml = A.pbm = A.pse = A.nav = A.gsum = 0.;
   A.bad_risk = false;
-  const double prevEq = A.cash + A.rAV - A.rBM;  // Env.h:190,208,234
+  const double prevEq = A.E;  // Env.h:190,208,234
   A.inv_prev = 1. / prevEq;
   A.rprod = 1.;
-  A.reduce_inloop = shaping && a.R.reduce_rewards && a.R.shaper != MDG_SHAPER_COSINE;
+  A.reduce_inloop = reduce_plain;
   // DQN.action_to_transaction (dqn.py:160-179) fused in front of the step: units from discrete actions and the
   // availableMargin of the incoming portfolio (Portfolio.cpp:229-231), one scale for every asset
-  // (a template parameter: the three extra live values cost 3 % in the units kernel at its 128-register budget)
   const int8_t* arow = (ACTIONS && mode == MDG_MODE_MULTI && a.IO.actions) ? a.IO.actions + e * na : nullptr;
-  const double act_scale = arow ? a.L.unit_size * (((A.cash + A.rSE) + (A.rAV - A.rML)) / P.required_margin) : 0.;
+  const double act_scale = arow ? a.L.unit_size * (A.X / P.required_margin) : 0.;
   const int act_half = a.L.action_atoms / 2;
 
-  StepConsts c;
-  c.reqM = P.required_margin;
-  c.maintM = P.maintenance_margin;
-  c.reqM_ok = c.reqM > 0. && c.reqM <= 1e6;
-  c.band_scale = 1e-9 * (1. + fabs(c.maintM)) * (c.reqM > 1. ? c.reqM : 1.);
-  c.g1 = 6. + 3. * fabs(P.slippage_rel) + fabs(P.tcost_rel);
-  c.g2 = 3. * fabs(P.slippage_abs);
-  c.force_exact = (a.L.flags & MDG_FLAG_FORCE_EXACT_GATE) != 0;
-  A.G += na * fabs(P.tcost_abs);  // the absolute cost of up to nA transactions
+  const StepConsts c = make_consts(a);
 
   const uint32_t gid = (uint32_t)(a.L.env_offset + e);
   const uint32_t k0 = (uint32_t)a.L.seed, k1 = (uint32_t)(a.L.seed >> 32);
   const uint32_t t_lo = (uint32_t)(uint64_t)ts, t_hi = (uint32_t)((uint64_t)ts >> 32);
 
   if (PAIRS) {
-    // ---- headline path: every asset belongs to an OU pair.  One iteration = one pair; the next pair's
-    // state and units are loaded while the current pair is processed (software prefetch).
+    // ---- headline path: every asset belongs to an OU pair.  One iteration = one pair.
     const int np = na >> 1;
     // This step's normals, all at once: the Philox + Box-Muller blocks are independent of each other and of
-    // the ledger, so they are generated four at a time (four interleaved dependency chains per thread --
-    // the kernel is latency-bound at one thread per env) while the first loads are in flight.
+    // the ledger, so they are generated four at a time (four interleaved dependency chains per thread)
+    // while the first loads are in flight.
     if (!a.IO.normals) {
       const int nslots = 3 * np, nblk = (nslots + 1) >> 1;
 #pragma unroll kRngUnroll
@@ -564,34 +612,33 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
 #pragma unroll 1
     for (int p = 0; p < np; ++p) {
       double price[2], cur[2], mep[2], bm[2], units[2], prev_val[2], tp[2], tu[2], tc[2];
-      int risk[2];
-      // the pair's state arrived through the prefetch stage p & 1 (group p; at most group p+1 is still in flight)
-      double mean;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int64_t o = (int64_t)(2 * p + q) * N + e;
         price[q] = S.price[o]; cur[q] = S.ledger[o]; mep[q] = S.mean_entry[o]; bm[q] = S.borrowed[o];
       }
-      if (units_v2) {
-        const double2 u2 = __ldcg(reinterpret_cast<const double2*>(urow + 2 * p));
-        units[0] = u2.x; units[1] = u2.y;
-      } else {
-        units[0] = (mode == MDG_MODE_MULTI && !arow) ? urow[2 * p] : 0.;
-        units[1] = (mode == MDG_MODE_MULTI && !arow) ? urow[2 * p + 1] : 0.;
-      }
+      units[0] = (mode == MDG_MODE_MULTI && !arow) ? urow[2 * p] : 0.;
+      units[1] = (mode == MDG_MODE_MULTI && !arow) ? urow[2 * p + 1] : 0.;
       if (arow) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) units[q] = action_units(arow[2 * p + q], act_half, act_scale, price[q], cur[q]);
       }
-      mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
+      if (mode == MDG_MODE_SINGLE) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) units[q] = (2 * p + q == a.L.asset_idx) ? urow[0] : 0.;
+      }
+      double mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
       if (p + MDG_PFDIST < np) prefetch_hint(p + MDG_PFDIST);
+      // PLAN both orders (independent of each other and of the chain), then GATE them in order
+      Plan o[2];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const int i = 2 * p + q;
-        if (mode == MDG_MODE_SINGLE) units[q] = (i == a.L.asset_idx) ? urow[0] : 0.;
-        tx_asset(a, c, A, N, e, na, i, price[q], cur[q], mep[q], bm[q], units[q], tp[q], tu[q], tc[q], risk[q],
-                 prev_val[q]);
+        prev_val[q] = cur[q] * price[q];  // offpolicy_q.py:141
+        plan_order(P, c, price[q], cur[q], mep[q], bm[q], units[q], o[q]);
       }
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        gate_apply(a, c, A, o[q], N, e, na, 2 * p + q, price[q], cur[q], mep[q], bm[q], units[q], tp[q], tu[q], tc[q]);
       // OUPair::getData, DataSource.cpp:1232-1240 (draw order rw, x0, x1)
       const MdgAssetGen& g0 = P.gen[2 * p];
       const MdgAssetGen& g1 = P.gen[2 * p + 1];
@@ -606,7 +653,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
         z1 = st[(4 * p + 2) * BS];
       }
       mean += mean * (z_rw * g0.p[2]);
-      gst(&S.gstate[(int64_t)g0.gslot * N + e], mean);
+      S.gstate[(int64_t)g0.gslot * N + e] = mean;
       const double newp0 = price[0] + ((g0.p[0] * (mean - price[0])) + mean * (z0 * g0.p[1]));
       const double newp1 = price[1] + ((g1.p[0] * (mean - price[1])) + mean * (z1 * g1.p[1]));
       post_tick<true, BS>(a, A, N, e, na, 2 * p, cur[0], newp0, prev_val[0], tp[0], tu[0], tc[0], st);
@@ -630,9 +677,11 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       if (arow) units = action_units(arow[i], act_half, act_scale, price, cur);
       else if (mode == MDG_MODE_MULTI) units = urow[i];
       else if (mode == MDG_MODE_SINGLE && i == a.L.asset_idx) units = urow[0];
-      double tp, tu, tc, prev_val;
-      int risk;
-      tx_asset(a, c, A, N, e, na, i, price, cur, mep, bm, units, tp, tu, tc, risk, prev_val);
+      double tp, tu, tc;
+      const double prev_val = cur * price;
+      Plan o;
+      plan_order(P, c, price, cur, mep, bm, units, o);
+      gate_apply(a, c, A, o, N, e, na, i, price, cur, mep, bm, units, tp, tu, tc);
       // generator tick of this asset (DataSource.cpp getData family)
       const MdgAssetGen& g = P.gen[i];
       double newp;
@@ -659,19 +708,19 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   const int head = a.L.head;
   // BrokerResponse.marginCall (Broker.cpp:135,156): Portfolio::checkRisk() after the last transaction
   if (mode != MDG_MODE_HOLD) a.IO.margin_call[e] = margin_call(cash, A.pav, pml, pbm, pse, maintM) ? 1 : 0;
-  gst(&S.cash[e], cash);
-  gst(&S.timestamp[e], ts + 1);
-  gst(&S.folds[(int64_t)MDG_FOLD_AV * N + e], nav);
-  gst(&S.folds[(int64_t)MDG_FOLD_ML * N + e], pml);
-  gst(&S.folds[(int64_t)MDG_FOLD_BM * N + e], pbm);
-  gst(&S.folds[(int64_t)MDG_FOLD_SE * N + e], pse);
-  gst(&S.folds[(int64_t)MDG_FOLD_G * N + e], fabs(cash) + A.gsum);
+  S.cash[e] = cash;
+  S.timestamp[e] = ts + 1;
+  S.folds[(int64_t)MDG_FOLD_AV * N + e] = nav;
+  S.folds[(int64_t)MDG_FOLD_ML * N + e] = pml;
+  S.folds[(int64_t)MDG_FOLD_BM * N + e] = pbm;
+  S.folds[(int64_t)MDG_FOLD_SE * N + e] = pse;
+  S.folds[(int64_t)MDG_FOLD_G * N + e] = fabs(cash) + A.gsum;
   const bool bad_risk = A.bad_risk;
 
   // ---- equity, reward, done (Env.h:192-198, 211-223, 237-249)
   const double currentEq = cash + nav - pbm;
   const double clampv = (mode == MDG_MODE_SINGLE) ? 0.01 : 0.3;
-  gst(&a.IO.reward[e], fast_log(dmax(currentEq / prevEq, clampv)));
+  a.IO.reward[e] = fast_log(dmax(currentEq / prevEq, clampv));
   const bool mc = margin_call(cash, nav, pml, pbm, pse, maintM);
   bool done = mc || (currentEq < 0.1 * P.init_cash);
   if (mode != MDG_MODE_HOLD) done = done || bad_risk;
@@ -691,11 +740,10 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   // ---- State.portfolio row = ledgerNormedFull (Portfolio.cpp:150-155).  Observations carry a 1e-9 bar
   // (not bit-exactness): the nA+1 divisions by equity are one reciprocal and nA+1 multiplies.
   const double inv_eq = 1. / currentEq;
-  const bool cosine = shaping && a.R.shaper == MDG_SHAPER_COSINE;
   double cosv_pp = 0., cosv_qq = 0., cosv_pq = 0.;
   {
     const double w0 = (cash - pbm) * inv_eq;
-    gst(&a.IO.obs_port[((int64_t)head * (na + 1)) * N + e], w0);
+    a.IO.obs_port[((int64_t)head * (na + 1)) * N + e] = w0;
     if (cosine) {
       const double d0 = a.R.desired_portfolio[0];
       cosv_pp = w0 * w0; cosv_qq = d0 * d0; cosv_pq = w0 * d0;
@@ -710,7 +758,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   for (int j = 0; j < na; ++j) {
     const double cur_val = st[stash_cur_row<PAIRS>(j, na) * BS];
     const double w = cur_val * inv_eq;
-    gst(&a.IO.obs_port[((int64_t)head * (na + 1) + j + 1) * N + e], w);
+    a.IO.obs_port[((int64_t)head * (na + 1) + j + 1) * N + e] = w;
     if (cosine) {
       const double dj = a.R.desired_portfolio[j + 1];
       cosv_pp = cosv_pp + w * w; cosv_qq = cosv_qq + dj * dj; cosv_pq = cosv_pq + w * dj;
@@ -719,8 +767,8 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       double x = (cur_val - st[stash_pm_row<PAIRS>(j, na) * BS]) * inv_prev;
       x += 1;
       const double r = fast_log((x != x) ? x : ((x < .35) ? .35 : x));
-      gst(&a.IO.agent_reward[(int64_t)j * N + e], r);
-      shaper_add(a, e, j, ra, r, done, len_before, len_after, n_popped);
+      a.IO.agent_reward[(int64_t)j * N + e] = r;
+      shaper_add(a, e, true, j, ra, r, done, len_before, len_after, n_popped);
     }
   }
   // reduced reward: sum_j log(x_j) as log(prod_j x_j) -- one log instead of nA (each x_j is in [.35, ~1.x] and
@@ -738,17 +786,17 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
         rprod = (j == 0) ? x : rprod * x;
       } else {
         const double r = fast_log(x);
-        gst(&a.IO.agent_reward[(int64_t)j * N + e], r);
-        shaper_add(a, e, j, ra, r + extra, done, len_before, len_after, n_popped);
+        a.IO.agent_reward[(int64_t)j * N + e] = r;
+        shaper_add(a, e, true, j, ra, r + extra, done, len_before, len_after, n_popped);
       }
     }
     if (a.R.reduce_rewards) {
       rsum = fast_log(rprod);
-      gst(&a.IO.agent_reward[e], rsum);
-      shaper_add(a, e, 0, 1, rsum + extra, done, len_before, len_after, n_popped);
+      a.IO.agent_reward[e] = rsum;
+      shaper_add(a, e, true, 0, 1, rsum + extra, done, len_before, len_after, n_popped);
     }
   } else if (inline_shaper) {  // nstep == 1: add, pop at once (shaper_add / shaper_pop with len == n == 1, same arithmetic)
-    gst(&a.IO.agent_reward[e], rsum);
+    a.IO.agent_reward[e] = rsum;
     double sh;
     const double d0 = a.R.discounts[0];
     if (a.R.shaper == MDG_SHAPER_DSR) {         // nstep_buffer.py:62-91
@@ -772,12 +820,12 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       sh = 0.;
       sh = sh + d0 * rsum;
     }
-    gst(&a.IO.shaped_reward[e], sh);
+    a.IO.shaped_reward[e] = sh;
     n_popped = 1;
-    if (moments) { gst(&a.S.shaper_A[e], shA); gst(&a.S.shaper_B[e], shB); }
-  } else if (shaping && a.R.reduce_rewards) {
-    gst(&a.IO.agent_reward[e], rsum);
-    shaper_add(a, e, 0, 1, rsum, done, len_before, len_after, n_popped);
+    if (moments) { a.S.shaper_A[e] = shA; a.S.shaper_B[e] = shB; }
+  } else if (reduce_plain) {
+    a.IO.agent_reward[e] = rsum;
+    shaper_add(a, e, true, 0, 1, rsum, done, len_before, len_after, n_popped);
   }
   if (shaping) {
     if (a.R.nstep > 1) S.nstep_len[e] = len_after;
@@ -785,8 +833,17 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   }
 }
 
+#ifndef MDG_MAXNREG_SMALL
+#define MDG_MAXNREG_SMALL 0  // > 0: explicit register cap of the one-wave variant instead of the launch-bounds one
+#endif
 template <bool PAIRS, int BS, int MINB, bool ACTIONS>
-__global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void
+#if MDG_MAXNREG_SMALL > 0
+__launch_bounds__(BS) __maxnreg__(MINB == MDG_MINB_SMALL ? MDG_MAXNREG_SMALL : 65536 / (BS * MINB) / 8 * 8)
+#else
+__launch_bounds__(BS, MINB)
+#endif
+step_kernel(const __grid_constant__ StepArgs a) {
   step_body<PAIRS, BS, ACTIONS>(a);
 }
 
@@ -815,18 +872,23 @@ static inline int launch_step(StepArgs& a) {
   const int64_t N = a.L.n_envs;
   cudaStream_t st = (cudaStream_t)a.L.stream;
   const bool pairs = all_ou_pairs(a.P);
-  const unsigned grid = (unsigned)((N + 127) / 128);
-  a.units_v2 = (a.IO.units && (reinterpret_cast<uintptr_t>(a.IO.units) & 15) == 0 && a.P.n_assets % 2 == 0) ? 1 : 0;
-  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
+  for (int i = 0; i < a.P.n_assets; ++i) {  // a role-1 asset must directly follow its role-0 partner
+    const MdgAssetGen& g = a.P.gen[i];
+    if (g.type == MDG_GEN_OUPAIR && g.role == 1 &&
+        (i == 0 || a.P.gen[i - 1].type != MDG_GEN_OUPAIR || a.P.gen[i - 1].role != 0))
+      return set_err(MDG_E_INVALID, "OUPair assets must be adjacent (role 0, role 1)");
+  }
+  const unsigned grid = (unsigned)((N + kBlock - 1) / kBlock);
+  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * kBlock;
   const bool acts = a.L.mode == MDG_MODE_MULTI && a.IO.actions;
   const bool small = N <= 148 * 512 * 2;  // up to two waves at 4 blocks per SM
-#define MDG_LAUNCH(PAIRS_, MINB_, ACT_) step_kernel<PAIRS_, 128, MINB_, ACT_><<<grid, 128, smem, st>>>(a)
+#define MDG_LAUNCH(PAIRS_, MINB_, ACT_) step_kernel<PAIRS_, kBlock, MINB_, ACT_><<<grid, kBlock, smem, st>>>(a)
   if (small) {
-    if (pairs) { if (acts) MDG_LAUNCH(true, 4, true); else MDG_LAUNCH(true, 4, false); }
-    else { if (acts) MDG_LAUNCH(false, 4, true); else MDG_LAUNCH(false, 4, false); }
+    if (pairs) { if (acts) MDG_LAUNCH(true, MDG_MINB_SMALL, true); else MDG_LAUNCH(true, MDG_MINB_SMALL, false); }
+    else { if (acts) MDG_LAUNCH(false, MDG_MINB_SMALL, true); else MDG_LAUNCH(false, MDG_MINB_SMALL, false); }
   } else {
-    if (pairs) { if (acts) MDG_LAUNCH(true, 3, true); else MDG_LAUNCH(true, 3, false); }
-    else { if (acts) MDG_LAUNCH(false, 3, true); else MDG_LAUNCH(false, 3, false); }
+    if (pairs) { if (acts) MDG_LAUNCH(true, MDG_MINB_LARGE, true); else MDG_LAUNCH(true, MDG_MINB_LARGE, false); }
+    else { if (acts) MDG_LAUNCH(false, MDG_MINB_LARGE, true); else MDG_LAUNCH(false, MDG_MINB_LARGE, false); }
   }
 #undef MDG_LAUNCH
   return cuda_err(cudaGetLastError(), "mdg_step launch");
