@@ -37,7 +37,13 @@ MARGINS = dict(required_margin=1., maintenance_margin=.25)
 COSTS = dict(transaction_cost_rel=.02, transaction_cost_abs=0., slippage_rel=.001, slippage_abs=0.)
 UNIT = 0.05 * 1_000_000. / 10.  # unit_size_proportion_avM .05 of init cash at the start price 10 (config.yaml:46)
 SEED = 0x6d616469_67616e00 ^ 5
-SETUP_STEPS = 64  # untimed steps per slab before the --warmup steps (see run())
+# Untimed steps per slab before the --warmup steps (see run_ours()).  The workload is not stationary at first: every
+# env starts an episode at the same tick and the random policy ruins ~3 % of them per step, in waves; the finished
+# share -- each a reset with a 64-tick history fill, ~half the cost of a step kernel at 3 % -- decays slowly as the
+# population mixes: 3.0 % after 64 steps, 1.4 % after 256, 0.7 % after 1,024, 0.4 % after 4,096 (profiles/r2_notes.md).
+# 2,048 steps per slab (~0.6 s) put the timed region into the long-run regime a training run spends its life in; the
+# line reports the share it saw (config.done_rate_last_step).
+SETUP_STEPS = 2048
 
 
 def bytes_per_env_step(nA=N_ASSETS, G=8, R=2, ra=1, sh=1):
@@ -206,22 +212,57 @@ def port_rate(sample_envs=8192, sample_steps=24, threads=None):
                       f"64-tick history fill, agent reward + DSR), oracle/mdg_oracle.c with OpenMP over envs, {dt:.2f} s"}
 
 
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("mdg_step_kernel.cuh", "mdg_common.cuh", "mdg_math.cuh"):
+        h.update(open(os.path.join(ROOT, "madigan_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE step-kernel launch of this workload, from the committed
-    `ncu --set full` capture (profiles/step_kernel_traffic.json names the report it was read from); bytes."""
+    `ncu --set full` capture (profiles/step_kernel_traffic.json names the report it was read from and the hash of the
+    kernel sources it was taken with); bytes.  None when the kernel sources have changed since that capture."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "step_kernel_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
             d = json.load(f)
+        if d.get("kernel_source_hash") != kernel_source_hash():
+            return None
         return d["dram_bytes_read"] + d["dram_bytes_write"]
     except Exception:
         return None
 
 
-def config_dict(n_gpus, slabs):
+def pin_to_gpu_numa_node(local):
+    """Bind this process to the host cores nearest to GPU `local` (NVML's CPU affinity), before any pinned buffer is
+    allocated: first-touch then places the staging buffers on the GPU's NUMA node, and 8 ranks stop sharing one
+    root complex for their H2D streams.  Returns the number of cores, or None when NVML says nothing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local])
+                                              if os.environ.get("CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit()
+                                              else local)
+        n = (os.cpu_count() or 1)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * w + b for w, x in enumerate(words) for b in range(64) if (x >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            pin_to_gpu_numa_node.before = allowed
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def config_dict(n_gpus, slabs, setup_steps=SETUP_STEPS):
     return {"workload": "C5 shape: 65,536 envs/GPU x 16-asset portfolios (8 OU pairs), cost .02 + slippage .001, "
                         "DSR reward n=1, 64-step observation ring, auto-reset on done",
             "envs_per_gpu": ENVS_PER_GPU, "n_assets": N_ASSETS, "window": WINDOW, "reward": "DSR(adaptation .001, n=1, reduced)",
-            "slabs_per_gpu": slabs, "setup_steps_per_slab": SETUP_STEPS, "l2": f"rotating {slabs} slabs of 65,536 envs: resident state "
+            "slabs_per_gpu": slabs, "setup_steps_per_slab": setup_steps, "l2": f"rotating {slabs} slabs of 65,536 envs: resident state "
                                           f"{slabs} x 40 MB + rings exceeds the 126 MB L2, each step runs cold",
             "bytes_per_env_step": bytes_per_env_step(), "parallelism": f"env-slab sharding x{n_gpus}, no step-path collective"}
 
@@ -233,9 +274,12 @@ def run_ours(args):
 
     rank, world, local = parallel.init_from_env("nccl")
     assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    numa_cores = pin_to_gpu_numa_node(local)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     slabs, K, W = args.slabs, args.steps, args.warmup
+    if slabs % max(1, min(args.streams, slabs)) != 0:
+        raise SystemExit("--slabs must be a multiple of --streams (a slab always runs on the same stream)")
     per_rank = ENVS_PER_GPU * slabs
     envs = [make_env(dev, rank * per_rank + s * ENVS_PER_GPU) for s in range(slabs)]
     acts = synth_actions(8, ENVS_PER_GPU, 1234 + rank, device=dev)
@@ -251,19 +295,15 @@ def run_ours(args):
     n_str = max(1, min(args.streams, slabs))
     streams = [torch.cuda.Stream(dev) for _ in range(n_str)]
 
-    fixed_streams = slabs % n_str == 0  # then slab i always runs on stream i % n_str: bind it once
-    if fixed_streams:
+    def bind_all():  # slab i always runs on stream i % n_str: every launch and staging copy of the env follows it
         for i_, e_ in enumerate(envs):
             e_.bind_stream(streams[i_ % n_str])
 
+    bind_all()
+
     def step_slab(i, acts_i):
-        env = envs[i % slabs]
         # the fused step kernel (dominant kernel) + masked auto-reset with history fill: one host call
-        if fixed_streams:
-            env.step(acts_i, auto_reset=True)
-        else:
-            with torch.cuda.stream(streams[i % n_str]):
-                env.step(acts_i, auto_reset=True)
+        envs[i % slabs].step(acts_i, auto_reset=True)
 
     def fork(ev):
         for st in streams:
@@ -281,35 +321,77 @@ def run_ours(args):
     # setup, untimed and independent of --warmup: every slab runs SETUP_STEPS steps, which allocates the per-stream
     # reset workspaces, loads the kernels and takes the slabs out of the synchronised start (all envs begin an episode
     # at the same tick, so the first ~40 steps see waves of simultaneous resets)
-    for i in range(SETUP_STEPS * slabs):
+    for i in range(args.setup_steps * slabs):
         step_slab(i, acts[i % len(acts)])
     for i in range(W):
         step_slab(i, acts[i % len(acts)])
     join()
     barrier()
 
-    # ---- timed region 1: device-resident inputs ("value")
+    # ---- timed region 1: device-resident inputs ("value").  The K steps are issued R times (`--repeats`); the line
+    # reports the MEDIAN repeat.  With `--graph` (default for K <= 512) the K-step sequence of a repeat -- 2 launches
+    # per step, forked over the streams -- is captured into one CUDA graph beforehand and the timed region is its
+    # launch: a 20-step region is ~1 ms of device work, less than the host needs to enqueue 40 launches one by one.
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
+    R_ = max(1, args.repeats)
+    use_graph = args.graph == "on" or (args.graph == "auto" and K <= 512)
+    cap = torch.cuda.Stream(dev)  # capture origin stream
+    graphs = []
+    step_no = W
+    t_issue = None
+    if use_graph:
+        for r_ in range(R_):
+            g_ = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(dev)
+            with torch.cuda.stream(cap):
+                g_.capture_begin(capture_error_mode="thread_local")
+                ev_f = torch.cuda.Event()
+                ev_f.record(cap)
+                for st in streams:
+                    st.wait_event(ev_f)
+                for i in range(K):
+                    step_slab(step_no + i, acts[i % len(acts)])
+                for st in streams:
+                    e_ = torch.cuda.Event()
+                    e_.record(st)
+                    cap.wait_event(e_)
+                g_.capture_end()
+            step_no += K
+            graphs.append(g_)
     launches0 = sum(e.launches for e in envs)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_all = []
     barrier()
     t_region0 = time.perf_counter()
-    ev0.record(stream)
-    fork(ev0)
-    t_issue = time.perf_counter()
-    for i in range(K):
-        step_slab(W + i, acts[i % len(acts)])
-    t_issue = (time.perf_counter() - t_issue) / K * 1e3  # host time to enqueue one step (must stay below ms_per_step)
-    join()
-    ev1.record(stream)
-    barrier()
-    launches = sum(e.launches for e in envs) - launches0
-    ms_total = ev0.elapsed_time(ev1)
+    for r_ in range(R_):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if use_graph:
+            with torch.cuda.stream(cap):
+                ev0.record(cap)
+                graphs[r_].replay()
+                ev1.record(cap)
+        else:
+            ev0.record(stream)
+            fork(ev0)
+            t_i = time.perf_counter()
+            for i in range(K):
+                step_slab(step_no + i, acts[i % len(acts)])
+            t_i = (time.perf_counter() - t_i) / K * 1e3  # host time to enqueue one step (must stay below ms_per_step)
+            t_issue = t_i if t_issue is None else min(t_issue, t_i)
+            step_no += K
+            join()
+            ev1.record(stream)
+        barrier()
+        ms_all.append(ev0.elapsed_time(ev1))
+    launches = (2 * K * R_) if use_graph else (sum(e.launches for e in envs) - launches0)
+    launches //= R_
+    ms_total = sorted(ms_all)[len(ms_all) // 2]
     t_region1 = time.perf_counter()
     sampler.stop()
     clocks = sampler.summary(t_region0, t_region1)
+    del graphs
 
     # ---- the dominant kernel alone (roofline): the step kernel of consecutive slabs back to back on ONE stream,
     # CUDA events around every launch, resets outside the event pairs
@@ -318,7 +400,7 @@ def run_ours(args):
     KK = min(K, 200)
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KK)]
     for i in range(KK):
-        env = envs[(W + K + i) % slabs]
+        env = envs[(step_no + i) % slabs]
         k_ev[i][0].record(stream)
         env.step(acts[i % len(acts)])
         k_ev[i][1].record(stream)
@@ -333,18 +415,22 @@ def run_ours(args):
     host_reward = [torch.empty(ENVS_PER_GPU, dtype=torch.float64).pin_memory() for _ in range(n_str)]
     host_done = [torch.empty(ENVS_PER_GPU, dtype=torch.bool).pin_memory() for _ in range(n_str)]
 
+    bind_all()
+    set_stream = torch.cuda.set_stream  # (cheaper than a `with torch.cuda.stream(...)` context per call)
+
     def e2e_step(i):
         env = envs[i % slabs]
         j = i % n_str
-        with torch.cuda.stream(streams[j]):
-            _s, r, d, _ = env.step(host_acts[i % 4], auto_reset=True)          # H2D of the units inside
-            host_reward[j].copy_(env.shaped_reward[0, :, 0], non_blocking=True)  # D2H of the step's result
-            host_done[j].copy_(d, non_blocking=True)
+        set_stream(streams[j])
+        _s, r, d, _ = env.step(host_acts[i % 4], auto_reset=True)          # H2D of the units inside
+        host_reward[j].copy_(env.shaped_reward[0, :, 0], non_blocking=True)  # D2H of the step's result
+        host_done[j].copy_(d, non_blocking=True)
 
     ev_w.record(stream)
     fork(ev_w)
     for i in range(max(2 * slabs, W // 2)):  # every slab at least twice (first calls allocate staging buffers)
         e2e_step(i)
+    set_stream(stream)
     join()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -352,6 +438,7 @@ def run_ours(args):
     fork(e0)
     for i in range(K):
         e2e_step(i)
+    set_stream(stream)
     join()
     e1.record(stream)
     barrier()
@@ -367,15 +454,16 @@ def run_ours(args):
     def e2e_actions_step(i):
         env = envs[i % slabs]
         j = i % n_str
-        with torch.cuda.stream(streams[j]):
-            _s, r, d, _ = env.step_actions(host_a8[i % 4], action_atoms=3, unit_size=.05, auto_reset=True)
-            host_reward[j].copy_(env.shaped_reward[0, :, 0], non_blocking=True)
-            host_done[j].copy_(d, non_blocking=True)
+        set_stream(streams[j])
+        _s, r, d, _ = env.step_actions(host_a8[i % 4], action_atoms=3, unit_size=.05, auto_reset=True)
+        host_reward[j].copy_(env.shaped_reward[0, :, 0], non_blocking=True)
+        host_done[j].copy_(d, non_blocking=True)
 
     ev_w.record(stream)
     fork(ev_w)
     for i in range(max(2 * slabs, W // 2)):  # every slab at least twice (first calls allocate staging buffers)
         e2e_actions_step(i)
+    set_stream(stream)
     join()
     barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -383,10 +471,13 @@ def run_ours(args):
     fork(a0)
     for i in range(K):
         e2e_actions_step(i)
+    set_stream(stream)
     join()
     a1.record(stream)
     barrier()
     e2e_act_ms = a0.elapsed_time(a1)
+    for e_ in envs:
+        e_.bind_stream(None)
     h2d = ENVS_PER_GPU * N_ASSETS * 8
     d2h = ENVS_PER_GPU * 8 + ENVS_PER_GPU
 
@@ -411,7 +502,7 @@ def run_ours(args):
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(world, slabs),
+            "config": config_dict(world, slabs, args.setup_steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": which,
                          "kernel": "mdg::step_kernel<PAIRS=true, 128 threads, 4 blocks/SM>",
@@ -422,7 +513,10 @@ def run_ours(args):
                             "h2d_bytes_per_step": ENVS_PER_GPU * N_ASSETS, "d2h_bytes_per_step": d2h,
                             "api": "Env.step_actions(int8 actions, action_atoms=3, unit_size=.05): "
                                    "DQN.action_to_transaction fused in front of the step"},
-            "gpu_launches": launches, "host_issue_ms_per_step": t_issue, "clocks": clocks,
+            "gpu_launches": launches, "repeats": R_, "ms_per_repeat": ms_all,
+            "timed_region": ("one CUDA graph launch per repeat (K steps x 2 kernels, forked over the streams)"
+                             if use_graph else "K eager Env.step(auto_reset=True) calls"),
+            "host_issue_ms_per_step": t_issue, "host_cores_bound": numa_cores, "clocks": clocks,
             "episode_stats": parallel.summarize_stats(stats, N_ASSETS),
         }
         es = line["episode_stats"]
@@ -430,8 +524,14 @@ def run_ours(args):
         # policy ruins ~3 % of the envs per step early on and fewer once the survivors' equity has grown
         line["config"]["done_rate_last_step"] = es["n_done"] / max(es["n_envs"], 1)
         if world == 1 and not args.no_cpu_baseline:
+            # in a subprocess: the reference's code is never loaded into the process that holds the product library
             try:
-                line["cpu_baseline"] = cpu_baseline()
+                before = getattr(pin_to_gpu_numa_node, "before", None)  # the baseline may use every host core again
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5",
+                                      "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                                     preexec_fn=(lambda: os.sched_setaffinity(0, before)) if before else None)
+                ref_line = json.loads(out.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref_line["cpu_baseline"]
             except Exception as ex:  # the oracle is test infrastructure; never let it break the GPU number
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line))
@@ -473,8 +573,7 @@ def run_reference(args):
     else:
         r = port_rate(8192, max(4, min(args.steps, 40)), threads)
         value, sample, ms_per_step = r["value"], r["sample"], 8192 / r["value"] * 1e3
-    cfg["reference_sample"] = sample
-    line = {"impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s",
+    line = {"impl": "reference", "reference_sample": sample, "metric": "env-steps/sec", "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
@@ -492,6 +591,10 @@ def main():
     ap.add_argument("--slabs", type=int, default=8)
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--setup-steps", type=int, default=SETUP_STEPS, help="untimed steps per slab before the warm-up")
+    ap.add_argument("--repeats", type=int, default=5, help="the K timed steps are issued this many times; the median is reported")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="timed region as one CUDA graph launch (auto: when --steps <= 512)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -467,7 +467,11 @@ static int fill_ws_args(ResetWsArgs& a, const MdgParams* P, const MdgState* S, c
 static int launch_fill(const ResetWsArgs& a, int64_t max_listed) {
   // the count is on the device: size the grid for the most the list can hold, capped at a few blocks per SM
   // (grid-stride; blocks past the end of the list only read the count and take their exit ticket)
-  const int64_t cap = 148 * 8;
+  static const int64_t cap = []() {  // MDG_FILL_GRID: profiling knob
+    const char* v = getenv("MDG_FILL_GRID");
+    const long n = v ? atol(v) : 0;
+    return (int64_t)(n > 0 ? n : 148 * 8);
+  }();
   const unsigned grid = (unsigned)(max_listed < cap ? (max_listed > 0 ? max_listed : 1) : cap);
   const size_t smem = sizeof(double) * (size_t)a.chunk * (size_t)(a.P.n_normals > 0 ? a.P.n_normals : 1);
   reset_fill_kernel<<<grid, kFillBlock, smem, (cudaStream_t)a.L.stream>>>(a);

@@ -84,14 +84,29 @@ __global__ void __launch_bounds__(128) replay_sample_kernel(const __grid_constan
       const unsigned long long j = (unsigned long long)(((x0 >> 11) * 0x1.0p-53) * (double)filled);
       const long long cand = (long long)(j < filled ? j : filled - 1);
       // the observation slot of the state must not have been overwritten: it survives `depth` steps
-      if (r.t_state_step[cand] > a.cur_step - r.depth && r.t_state_step[cand] >= 0) { pick = cand; break; }
+      const long long sstep = r.t_state_step[cand];  // LLONG_MIN = never written (step -1 is observe_start's slot)
+      if (sstep != (-9223372036854775807LL - 1) && sstep > a.cur_step - r.depth) { pick = cand; break; }
     }
     s_idx = pick;
   }
   __syncthreads();
   const long long idx = s_idx;
   if (threadIdx.x == 0) a.out.idx[b] = idx;
-  if (idx < 0) return;
+  if (idx < 0) {  // no resident transition found: a zero row, flagged by idx = -1 and masked by done = 1
+    const int64_t o_b = b * a.welems;
+    if (a.dtype == MDG_DTYPE_F32) {
+      float* d0 = (float*)a.out.state_price; float* d1 = (float*)a.out.next_price;
+      for (int i = threadIdx.x; i < a.welems; i += 128) { d0[o_b + i] = 0.f; d1[o_b + i] = 0.f; }
+    } else {
+      double* d0 = (double*)a.out.state_price; double* d1 = (double*)a.out.next_price;
+      for (int i = threadIdx.x; i < a.welems; i += 128) { d0[o_b + i] = 0.; d1[o_b + i] = 0.; }
+    }
+    for (int i = threadIdx.x; i < a.n_port; i += 128) { a.out.state_port[b * a.n_port + i] = 0.; a.out.next_port[b * a.n_port + i] = 0.; }
+    for (int i = threadIdx.x; i < r.n_action; i += 128) a.out.action[b * r.n_action + i] = 0.;
+    for (int i = threadIdx.x; i < r.ra; i += 128) a.out.reward[b * r.ra + i] = 0.;
+    if (threadIdx.x == 0) a.out.done[b] = 1;
+    return;
+  }
   const int64_t e = r.t_env[idx];
   const int64_t ss = r.t_state_slot[idx], sn = r.t_next_slot[idx];
   const int64_t o_s = (ss * a.N + e) * a.welems, o_n = (sn * a.N + e) * a.welems, o_b = b * a.welems;

@@ -74,7 +74,7 @@ _RESET_WS = {}
 _RESET_NEED = {}
 
 
-def _reset_workspace(lib_, P, n_envs, fill_ticks, device, stream_ptr=None):
+def _reset_workspace(lib_, P, n_envs, fill_ticks, device, stream_ptr=None, stream=None):
     nk = (P.n_normals, n_envs, fill_ticks)
     need = _RESET_NEED.get(nk)
     if need is None:
@@ -84,6 +84,9 @@ def _reset_workspace(lib_, P, n_envs, fill_ticks, device, stream_ptr=None):
     if ws is None or ws.numel() < need:
         # the 256-byte header {list length, exit ticket} must be zero before the first use; the kernels leave it zero
         ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        if stream is not None:  # zeroed on torch's current stream, used on the bound one
+            stream.wait_stream(torch.cuda.current_stream(device))
+            ws.record_stream(stream)
         _RESET_WS[key] = ws
     return ws
 
@@ -196,15 +199,25 @@ class Env:
         L.nstep_pos = self._gstep % self.R.nstep
         L.seed = self.seed
         L.env_offset = self.env_offset
-        L.stream = self._stream_ptr if self._stream_ptr is not None else _raw_stream(self.device.index)
+        L.stream = self._sptr()
         L.flags = self.flags
         return L
+
+    def _sptr(self):
+        """cudaStream_t every launch of this env goes to: the bound stream, else torch's current stream."""
+        return self._stream_ptr if self._stream_ptr is not None else _raw_stream(self.device.index)
+
+    def _copy_ctx(self):
+        """`with` context for torch ops that must run on this env's stream (staging copies)."""
+        return _NULL_CTX if self._stream is None else torch.cuda.stream(self._stream)
 
     def bind_stream(self, stream):
         """Pin this env's launches to ``stream`` (a torch.cuda.Stream; None = torch's current stream again).
         A driver that steps several slabs round-robin, one stream per slab, then needs no stream context manager
-        per call (which costs more host time than the step itself); inputs must already be on the device, or be
-        copied by the caller on that stream."""
+        per call (which costs more host time than the step itself).  EVERY launch of the env follows the binding --
+        step, reset, derived accounting, window / time materialisation, episode statistics, and the kernels of a
+        DeviceReplay built on it -- and so do the staging copies of host inputs.  Tensors the env returns are
+        produced on that stream: a consumer on another stream must wait for it (``other.wait_stream(stream)``)."""
         self._stream = stream
         self._stream_ptr = None if stream is None else stream.cuda_stream
 
@@ -260,7 +273,7 @@ class Env:
             m = m.to(device=self.device, dtype=torch.uint8).contiguous()
             if tuple(m.shape) != (self.N,):
                 raise ValueError(f"mask must have shape ({self.N},)")
-        ws = _reset_workspace(self._lib, self.P, self.N, int(fill_ticks), self.device, self._stream_ptr)
+        ws = _reset_workspace(self._lib, self.P, self.N, int(fill_ticks), self.device, self._stream_ptr, self._stream)
         check(self._lib.mdg_reset_ws(C.byref(self.P), C.byref(self._S), C.byref(io), C.byref(self._launch()),
                                      None if m is None else m.data_ptr(), int(fill_ticks), int(clear_nstep),
                                      ws.data_ptr(), ws.numel()))
@@ -319,7 +332,8 @@ class Env:
                         raise ValueError(f"units must have shape {tuple(want)}, got {tuple(u.shape)}")
                 if not u.is_cuda or u.device != self.device or not u.is_contiguous():
                     dst = self.t["units"] if mode == A.MODE_MULTI else self.t["units"].view(-1)[:self.N]
-                    dst.copy_(u, non_blocking=True)  # H2D from (pinned) host memory, async on this stream
+                    with self._copy_ctx():
+                        dst.copy_(u, non_blocking=True)  # H2D from (pinned) host memory, async on the env's stream
                     u = dst
                 io.units = u.data_ptr()
             else:
@@ -329,11 +343,12 @@ class Env:
                 keep = None
             else:
                 io.normals, io.uniforms, keep = self._noise(normals, uniforms)
+            head0 = self.head
             self.head = (self.head + 1) % self.k
-            self.n_valid = min(self.k, self.n_valid + 1)
             L = self._launch(mode, asset_idx)
+            self.head = head0  # the ring head moves only once the launch has been accepted
             if auto_reset and keep is None:  # step + masked reset + history fill in one trip through the binding
-                ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr)
+                ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr, self._stream)
                 check(self._lib.mdg_step_autoreset(self._pP, self._pR, self._pS, self._pIO, self._pL, self.k, 1,
                                                    ws.data_ptr(), ws.numel()))
                 self.launches += 2  # step kernel (appends the finished envs to the list) + refill kernel
@@ -341,6 +356,8 @@ class Env:
             else:
                 check(self._lib.mdg_step(self._pP, self._pR, self._pS, self._pIO, self._pL))
                 self.launches += 1
+            self.head = L.head
+            self.n_valid = min(self.k, self.n_valid + 1)
             if mode != A.MODE_HOLD and self.R.shaper != A.SHAPER_OFF:
                 self._gstep += 1
             self._version += 1
@@ -368,7 +385,8 @@ class Env:
             if not a.is_cuda or a.device != self.device or not a.is_contiguous():
                 if "actions" not in self.t:
                     self.t["actions"] = torch.empty((self.N, self.nA), dtype=torch.int8, device=self.device)
-                self.t["actions"].copy_(a, non_blocking=True)
+                with self._copy_ctx():
+                    self.t["actions"].copy_(a, non_blocking=True)
                 a = self.t["actions"]
             io.units = None
             io.actions = a.data_ptr()
@@ -378,12 +396,13 @@ class Env:
                     keep = None
                 else:
                     io.normals, io.uniforms, keep = self._noise(normals, uniforms)
+                head0 = self.head
                 self.head = (self.head + 1) % self.k
-                self.n_valid = min(self.k, self.n_valid + 1)
                 L = self._launch(A.MODE_MULTI, 0)
+                self.head = head0
                 L.action_atoms, L.unit_size = int(action_atoms), float(unit_size)
                 if auto_reset and keep is None:
-                    ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr)
+                    ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr, self._stream)
                     check(self._lib.mdg_step_autoreset(self._pP, self._pR, self._pS, self._pIO, self._pL, self.k, 1,
                                                        ws.data_ptr(), ws.numel()))
                     self.launches += 1  # + the refill kernel
@@ -392,6 +411,8 @@ class Env:
                     check(self._lib.mdg_step(self._pP, self._pR, self._pS, self._pIO, self._pL))
             finally:
                 io.actions = None
+            self.head = L.head
+            self.n_valid = min(self.k, self.n_valid + 1)
             self.launches += 1
             if self.R.shaper != A.SHAPER_OFF:
                 self._gstep += 1
@@ -565,7 +586,7 @@ class Env:
                         timestamp=self.t["timestamp"].data_ptr(), reset_ts=self.t["reset_ts"].data_ptr(),
                         n_envs=self.N, n_feats=n_feats, window=self.k, head=self.head, n_valid=nv, norm_type=norm,
                         flat_prefix=flat_prefix, out_dtype=dt, out_layout=layout, out=out.data_ptr(),
-                        stream=torch.cuda.current_stream(self.device).cuda_stream, transform=transform)
+                        stream=self._sptr(), transform=transform)
         with torch.cuda.device(self.device):
             check(self._lib.mdg_materialise_window(C.byref(w)))
         self.launches += 1
@@ -583,7 +604,7 @@ class Env:
         out = torch.empty((self.N, nv), dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
             check(self._lib.mdg_materialise_time(self.t["timestamp"].data_ptr(), self.N, nv, out.data_ptr(),
-                                                 torch.cuda.current_stream(self.device).cuda_stream))
+                                                 self._sptr()))
         self.launches += 1
         return out
 
@@ -598,19 +619,32 @@ class Env:
         self.launches += 2
         return out
 
+    _STAGING = ("units", "actions")  # host-input staging buffers: not state
+
     def state_dict(self):
         """Checkpoint of the env (the reference cannot checkpoint its env: wall-clock seeded RNG)."""
-        sd = {k_: v.clone() for k_, v in self.t.items() if k_ != "units"}
+        sd = {k_: v.clone() for k_, v in self.t.items() if k_ not in self._STAGING}
         sd["_meta"] = dict(head=self.head, n_valid=self.n_valid, gstep=self._gstep, seed=self.seed,
-                           env_offset=self.env_offset)
+                           env_offset=self.env_offset, n_envs=self.N, n_assets=self.nA, window=self.k,
+                           nstep=int(self.R.nstep), ra=self.ra, shaper=int(self.R.shaper),
+                           margins=(self.P.required_margin, self.P.maintenance_margin),
+                           costs=(self.P.tcost_rel, self.P.tcost_abs, self.P.slippage_rel, self.P.slippage_abs))
         return sd
 
     def load_state_dict(self, sd):
+        m = sd["_meta"]
+        mine = dict(n_envs=self.N, n_assets=self.nA, window=self.k, nstep=int(self.R.nstep), ra=self.ra,
+                    shaper=int(self.R.shaper))
+        for k_, v in mine.items():
+            if k_ in m and m[k_] != v:
+                raise ValueError(f"checkpoint was taken from an Env with {k_}={m[k_]}, this one has {k_}={v}")
         for k_, v in sd.items():
-            if k_ == "_meta":
+            if k_ == "_meta" or k_ in self._STAGING or k_ not in self.t:
                 continue
             self.t[k_].copy_(v)
-        m = sd["_meta"]
         self.head, self.n_valid, self._gstep = m["head"], m["n_valid"], m["gstep"]
         self.seed, self.env_offset = m["seed"], m["env_offset"]
+        if "margins" in m:
+            self.P.required_margin, self.P.maintenance_margin = m["margins"]
+            self.P.tcost_rel, self.P.tcost_abs, self.P.slippage_rel, self.P.slippage_abs = m["costs"]
         self.invalidate()

@@ -31,7 +31,10 @@ class DeviceReplay:
             raise ValueError("DeviceReplay needs an Env built with reward=... (the step kernel makes the n-step rewards)")
         if self.depth <= self.nstep + 1:
             raise ValueError("depth must exceed nstep + 1")
-        self.capacity = int(capacity) if capacity else N * (self.depth - self.nstep - 1)
+        cap_max = N * (self.depth - self.nstep - 1)
+        self.capacity = int(capacity) if capacity else cap_max
+        if self.capacity > cap_max:  # older records would point at overwritten observation slots
+            raise ValueError(f"capacity {self.capacity} exceeds N * (depth - nstep - 1) = {cap_max}")
         self.n_action = int(n_action) if n_action else nA
         self.norm_type, self.dtype, self.seed = norm_type, dtype, int(seed)
         dev = env.device
@@ -40,7 +43,7 @@ class DeviceReplay:
         self.obs_port = torch.empty((self.depth, N, nA + 1), dtype=torch.float64, device=dev)
         self.t = dict(t_env=z(self.capacity, dt=torch.int32), t_state_slot=z(self.capacity, dt=torch.int32),
                       t_next_slot=z(self.capacity, dt=torch.int32),
-                      t_state_step=torch.full((self.capacity,), -1, dtype=torch.int64, device=dev),
+                      t_state_step=torch.full((self.capacity,), -2 ** 63, dtype=torch.int64, device=dev),  # INT64_MIN = empty
                       t_done=z(self.capacity, dt=torch.uint8), t_reward=z(self.capacity, self.ra, dt=torch.float64),
                       t_action=z(self.capacity, self.n_action, dt=torch.float64),
                       cursor=z(1, dt=torch.int64), act_ring=z(self.nstep, N, self.n_action, dt=torch.float64))
@@ -58,7 +61,8 @@ class DeviceReplay:
 
     def observe_start(self):
         """Store the observation the first action is taken from (after ``env.reset(fill_history=True)``)."""
-        self._store_obs(self.step_count)
+        with self.env._copy_ctx():
+            self._store_obs(self.step_count)
 
     def add(self, action):
         """Call after ``env.step(..., auto_reset=True)`` / ``env.step_actions(...)`` with the action that was taken
@@ -71,20 +75,22 @@ class DeviceReplay:
             torch.as_tensor(action).to(device=env.device, dtype=torch.float64).contiguous()
         if a.shape != (self.N, self.n_action):
             raise ValueError(f"action must have shape {(self.N, self.n_action)}")
-        self._store_obs(t)
+        with env._copy_ctx():
+            self._store_obs(t)
         T = env.t
         with torch.cuda.device(env.device):
             check(self._lib.mdg_replay_append(
                 C.byref(self._rp), self.N, t, a.data_ptr(), T["shaped_reward"].data_ptr(), T["n_popped"].data_ptr(),
-                T["nstep_len"].data_ptr() if self.nstep > 1 else None, env._done_u8.data_ptr(),
-                torch.cuda.current_stream(env.device).cuda_stream))
+                T["nstep_len"].data_ptr() if self.nstep > 1 else None, env._done_u8.data_ptr(), env._sptr()))
 
     def __len__(self):
         return min(int(self.t["cursor"].item()), self.capacity)
 
     # ------------------------------------------------------------------ sample
     def sample(self, n):
-        """``ReplayBuffer.sample`` (replay_buffer.py:94-103): (SARSD of batched tensors, None)."""
+        """``ReplayBuffer.sample`` (replay_buffer.py:94-103): (SARSD of batched tensors, None).  Runs on the env's
+        stream (``Env.bind_stream``).  ``self.last_valid`` flags the rows that hold a real transition (all of them
+        unless the ring is nearly empty or mostly stale)."""
         dev = self.env.device
         out = self._out.get(n)
         if out is None:  # output buffers are allocated once per batch size and reused (a sample is consumed by the
@@ -104,8 +110,11 @@ class DeviceReplay:
             check(self._lib.mdg_replay_sample(
                 C.byref(self._rp), self.N, self.step_count, self.obs_price.data_ptr(), self.obs_port.data_ptr(),
                 self.k * self.nF, self.n_port, A.DTYPE_F32 if self.dtype == torch.float32 else A.DTYPE_F64, n,
-                self.seed, self.draws, C.byref(b), torch.cuda.current_stream(dev).cuda_stream))
+                self.seed, self.draws, C.byref(b), self.env._sptr()))
         self.last_idx = out["idx"]
+        # (batch,) bool: False where 64 draws found no resident transition (the row is zero-filled with done = True)
+        with self.env._copy_ctx():
+            self.last_valid = out["idx"] >= 0
         sarsd = SARSD(State(out["state_price"], out["state_port"], None), out["action"], out["reward"],
                       State(out["next_price"], out["next_port"], None), out["done"].bool())
         return sarsd, None
