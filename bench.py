@@ -42,7 +42,7 @@ SEED = 0x6d616469_67616e00 ^ 5
 # share -- each a reset with a 64-tick history fill, ~half the cost of a step kernel at 3 % -- decays slowly as the
 # population mixes: 3.0 % after 64 steps, 1.4 % after 256, 0.7 % after 1,024, 0.4 % after 4,096 (profiles/r2_notes.md).
 # 2,048 steps per slab (~0.6 s) put the timed region into the long-run regime a training run spends its life in; the
-# line reports the share it saw (config.done_rate_last_step).
+# line reports the share it saw (done_rate_last_step).
 SETUP_STEPS = 2048
 
 
@@ -522,7 +522,7 @@ def run_ours(args):
         es = line["episode_stats"]
         # share of the envs that finished (and were reset with a 64-tick history fill) in the last step: the random
         # policy ruins ~3 % of the envs per step early on and fewer once the survivors' equity has grown
-        line["config"]["done_rate_last_step"] = es["n_done"] / max(es["n_envs"], 1)
+        line["done_rate_last_step"] = es["n_done"] / max(es["n_envs"], 1)  # (not in config: both arms print the same config)
         if world == 1 and not args.no_cpu_baseline:
             # in a subprocess: the reference's code is never loaded into the process that holds the product library
             try:
@@ -540,6 +540,181 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations (`--config c2|c3|c4|c5_1m`): parity-test cases first of all
+# (tests/test_baseline_configs.py); here each gets a bench line with its own roofline (SURVEY.md section 8d's
+# per-env-step bytes for ITS shape).  The driver's default run (`--config c5`, the metric's configuration) is unchanged.
+# ---------------------------------------------------------------------------------------------------------------
+COMPOSITE16 = {
+    "sines": {"data_source_type": "Synth", "data_source_config": {
+        "freq": [1., 0.3, 2., 0.5], "mu": [2., 2.1, 2.2, 2.3], "amp": [1., 1.2, 1.3, 1.],
+        "phase": [0., 1., 2., 1.], "dX": 0.01, "noise": 0.01}},
+    "ou": {"data_source_type": "OU", "data_source_config": {
+        "mean": [10., 5., 1., 2.], "theta": [.08, .15, .15, .1], "phi": [.04, .04, .04, .04]}},
+    "pair": {"data_source_type": "OUPair", "data_source_config": {"theta": .015, "phi": .01, "noise": .03}},
+    "trend": {"data_source_type": "SimpleTrend", "data_source_config": {
+        "trend_prob": [0.05, 0.02], "min_period": [5, 10], "max_period": [20, 30], "noise": [0.01, 0.005],
+        "start": [10., 15.], "dYMin": [0.001, 0.01], "dYMax": [0.003, 0.03]}},
+    "trendou": {"data_source_type": "TrendOU", "data_source_config": {
+        "trend_prob": [0.05, 0.02], "min_period": [5, 10], "max_period": [20, 30], "dYMin": [0.001, 0.01],
+        "dYMax": [0.003, 0.03], "start": [10., 15.], "theta": [.1, .05], "phi": [.02, .01],
+        "noise_trend": [.01, .012], "ema_alpha": [0.1, 0.2]}},
+    "trendyou": {"data_source_type": "TrendyOU", "data_source_config": {
+        "trend_prob": [0.05, 0.02], "min_period": [5, 10], "max_period": [20, 30], "dYMin": [0.001, 0.01],
+        "dYMax": [0.003, 0.03], "start": [10., 15.], "theta": [.1, .05], "phi": [.02, .01],
+        "noise_trend": [.01, .012], "ema_alpha": [0.1, 0.2]}},
+}
+WORKLOADS = {
+    # name: data source, envs (per GPU, or in total when "total"), nA, generator-state rows G, shaper moments R, ...
+    "c2": dict(what="C2: 4,096 single-asset OU envs, log-return reward, window 64", ds=("OU", {"mean": [10.], "theta": [.08], "phi": [.04]}),
+               envs=4096, nA=1, G=0, R=0, reward=dict(reward_shaper_config={"reward_shaper": None}, nstep_return=1, reduce_rewards=True),
+               margins=(1., .25), costs=(0., 0.), unit=5000., kernel="mdg::step_kernel<generic>"),
+    "c3": dict(what="C3: 65,536 OU-pair (2-asset stat-arb) envs/GPU, cost .02 + slippage .001, DSR n=1, window 64",
+               ds=("OUPair", {"theta": .015, "phi": .01, "noise": .03}), envs=65536, nA=2, G=1, R=2,
+               reward=dict(reward_shaper_config={"reward_shaper": "DSR", "adaptation_rate": .001}, nstep_return=1, reduce_rewards=True),
+               margins=(1., .25), costs=(.02, .001), unit=5000., kernel="mdg::step_kernel<PAIRS>"),
+    "c4": dict(what="C4: 65,536 composite-synth 16-asset portfolios/GPU (Synth4 + OU4 + OUPair + SimpleTrend2 + TrendOU2 + "
+                    "TrendyOU2), required margin .1, cost .001, PPC reward n=5 per asset, standard_normal fp32 window every step",
+               ds=("Composite", COMPOSITE16), envs=65536, nA=16, G=4 + 1 + 4 + 6 + 8, R=0,
+               reward=dict(reward_shaper_config={"reward_shaper": "cosine_port_shaper", "desired_portfolio": [1.] + [0.] * 16,
+                                                 "cosine_temp": .025}, nstep_return=5, reduce_rewards=False),
+               margins=(.1, .25), costs=(.001, 0.), unit=5000., window_norm="standard_normal", kernel="mdg::step_kernel<generic>"),
+    "c5_1m": dict(what="C5 sweep: 1,048,576 16-asset OU-pair portfolios IN TOTAL, sharded over the GPUs (one slab per GPU, one "
+                       "launch per step), cost .02 + slippage .001, DSR n=1, window 64, episode statistics all-reduced (NCCL) every "
+                       "1,000 steps inside the timed region",
+                  ds=("Composite", PAIRS), envs=1_048_576, total=True, nA=16, G=8, R=2, reward=REWARD, margins=(1., .25),
+                  costs=(.02, .001), unit=UNIT, stats_every=1000, setup=2048, kernel="mdg::step_kernel<PAIRS>"),
+}
+
+
+def run_workload(args):
+    """One bench line for a non-default BASELINE configuration: K eager `Env.step(units, auto_reset=True)` calls on one
+    slab per GPU (device-resident units; `e2e` repeats them with pinned-host units and a D2H read of reward/done)."""
+    import torch
+    import torch.distributed as dist
+    from madigan_b200 import parallel
+    from madigan_b200.environments import Env
+
+    wl = WORKLOADS[args.config]
+    rank, world, local = parallel.init_from_env("nccl")
+    pin_to_gpu_numa_node(local)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    total = bool(wl.get("total"))
+    if total:
+        off, n = parallel.shard_envs(wl["envs"], world, rank)
+    else:
+        off, n = rank * wl["envs"], wl["envs"]
+    nA, K, W = wl["nA"], args.steps, args.warmup
+    env = Env(wl["ds"][0], 1_000_000., {"data_source_config": wl["ds"][1]}, n_envs=n, window=WINDOW, seed=SEED,
+              device=dev, env_offset=off, reward=wl["reward"])
+    env.setRequiredMargin(wl["margins"][0]); env.setMaintenanceMargin(wl["margins"][1])
+    env.setTransactionCost(wl["costs"][0], 0.); env.setSlippage(wl["costs"][1], 0.)
+    env.reset(fill_history=True)
+    g = torch.Generator().manual_seed(77 + rank)
+    acts = [(torch.randint(-1, 2, (n, nA), generator=g).double() * wl["unit"]).to(dev) for _ in range(4)]
+    host_acts = [a.cpu().pin_memory() for a in acts[:2]]
+    norm = wl.get("window_norm")
+    wout = torch.empty((n, WINDOW, nA), dtype=torch.float32, device=dev) if norm else None
+    stats_every = wl.get("stats_every")
+    host_r = torch.empty(n, dtype=torch.float64).pin_memory()
+    host_d = torch.empty(n, dtype=torch.bool).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one(i, a):
+        env.step(a, auto_reset=True)
+        if norm:
+            env.window(norm, out=wout)
+        if stats_every and (i + 1) % stats_every == 0:
+            parallel.reduce_episode_stats(env.episode_stats(), nA)  # the only cross-GPU traffic, off the step path
+
+    setup = wl.get("setup", args.setup_steps_small)
+    for i in range(setup + W):
+        one(i, acts[i % 4])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ms_all = []
+    l0 = env.launches
+    t0 = time.perf_counter()
+    for r_ in range(max(1, args.repeats)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(K):
+            one(i, acts[i % 4])
+        e1.record()
+        barrier()
+        ms_all.append(e0.elapsed_time(e1))
+    t1 = time.perf_counter()
+    launches = (env.launches - l0) // max(1, args.repeats)
+    sampler.stop()
+    clocks = sampler.summary(t0, t1)
+    ms_total = sorted(ms_all)[len(ms_all) // 2]
+    # the dominant kernel alone: events around the step launch, the reset outside the pair
+    KK = min(K, 100)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KK)]
+    for i in range(KK):
+        ev[i][0].record()
+        env.step(acts[i % 4])
+        ev[i][1].record()
+        env._reset_launch(env.t["done"], WINDOW, True, None, None)
+    barrier()
+    kern_ms = sum(a.elapsed_time(b) for a, b in ev) / KK
+    # end to end with host buffers
+    for i in range(4):
+        env.step(host_acts[i % 2], auto_reset=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        _s, r, d, _ = env.step(host_acts[i % 2], auto_reset=True)
+        if norm:
+            env.window(norm, out=wout)
+        host_r.copy_(r, non_blocking=True)
+        host_d.copy_(d, non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    stats = parallel.reduce_episode_stats(env.episode_stats(), nA)
+    t = torch.tensor([ms_total, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kern_ms = (float(x) for x in t.cpu())
+    if rank == 0:
+        peak, which = peaks()
+        ra = 1 if wl["reward"]["reduce_rewards"] else nA
+        B = bytes_per_env_step(nA, wl["G"], wl["R"], ra)
+        n_all = wl["envs"] if total else wl["envs"] * world
+        line = {
+            "metric": "env-steps/sec", "value": n_all * K / (ms_total * 1e-3), "unit": "env-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+            "scaling": "strong" if total else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["what"], "envs_total": n_all, "envs_this_gpu": n, "n_assets": nA, "window": WINDOW,
+                       "bytes_per_env_step": B, "setup_steps": setup,
+                       "l2": "one slab per GPU stepped repeatedly: its state is %s the 126 MB L2" %
+                             ("larger than" if B * n > 126e6 else "SMALLER than (L2-warm, stated)"),
+                       "parallelism": f"env-slab sharding x{world}, no step-path collective"},
+            "roofline": {"bound": "hbm", "achieved": B * n / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": B * n / (kern_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": which,
+                         "kernel": wl["kernel"], "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": B * n},
+            "e2e": {"value": n_all * K / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * nA * 8,
+                    "d2h_bytes_per_step": n * 9},
+            "gpu_launches": launches, "repeats": max(1, args.repeats), "ms_per_repeat": ms_all, "clocks": clocks,
+            "episode_stats": parallel.summarize_stats(stats, nA),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+
 def run_reference(args):
     """The reference arm: the reference's own CPU implementation of the path on the box's host cores, all threads.
     oracle/_ref (the reference's C++ sources compiled unmodified against an Eigen shim) when it was built, else
@@ -548,7 +723,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    cfg = config_dict(args.gpus, args.slabs)
+    cfg = config_dict(args.gpus, args.slabs, args.setup_steps)
     kind = "port"
     try:
         from oracle import ref
@@ -591,6 +766,9 @@ def main():
     ap.add_argument("--slabs", type=int, default=8)
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c5", choices=["c5"] + sorted(WORKLOADS),
+                    help="c5 (default) = the metric's configuration; the others are BASELINE.json's remaining configurations")
+    ap.add_argument("--setup-steps-small", type=int, default=256, help="untimed steps before the warm-up (--config != c5)")
     ap.add_argument("--setup-steps", type=int, default=SETUP_STEPS, help="untimed steps per slab before the warm-up")
     ap.add_argument("--repeats", type=int, default=5, help="the K timed steps are issued this many times; the median is reported")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
@@ -598,6 +776,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "c5":
+        if args.steps == 4000:  # (the default of the c5 run)
+            args.steps = 200
+        run_workload(args)
     else:
         run_ours(args)
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 8
+#define MDG_ABI_VERSION 9
 #define MDG_MAX_ASSETS 16
 #define MDG_GEN_NPARAM 10
 #define MDG_MAX_NSTEP 64
@@ -178,6 +178,12 @@ typedef struct MdgStepIO {
                              as it stands before the first transaction:
                                units_i = (a_i - action_atoms/2) * ((unit_size * availableMargin) / price_i),
                                a_i == 0 closes the position (units_i = -ledger_i, or 0 when flat). */
+  const float *weights;   /* nullable, MDG_MODE_MULTI only: (N,nA+1) row-major fp32 target portfolio weights (cash first),
+                             what a DDPG actor emits.  When given, `units` and `actions` are ignored and the units are
+                             derived in the kernel as DDPG.action_to_transaction does (modelling/algorithm/ddpg.py:182-207)
+                             from the portfolio as it stands before the first transaction:
+                               desired = w / sum(w) (fp32; w itself when the sum is 0),
+                               units_i = ((desired_{i+1} - ledgerNormedFull_{i+1}) * equity) / price_i. */
 } MdgStepIO;
 
 #define MDG_MODE_HOLD 0   /* Env::step()            Env.h:189-204 */

@@ -5,7 +5,7 @@ checks the struct sizes against the compiled library (``mdg_sizeof``).
 """
 import ctypes as C
 
-MDG_ABI_VERSION = 8
+MDG_ABI_VERSION = 9
 FLAG_FORCE_EXACT_GATE = 1
 XFORM_NONE, XFORM_PAIR_RATIO, XFORM_RETURNS = 0, 1, 2
 MDG_MAX_ASSETS = 16
@@ -67,7 +67,7 @@ class MdgStepIO(C.Structure):
     _fields_ = [(n, _dp) for n in ("units", "normals", "uniforms", "obs_price", "obs_port",
                                    "pre_price", "reward", "done", "trans_price", "trans_units",
                                    "trans_cost", "risk", "margin_call", "agent_reward",
-                                   "shaped_reward", "n_popped", "actions")]
+                                   "shaped_reward", "n_popped", "actions", "weights")]
 
 
 class MdgLaunch(C.Structure):

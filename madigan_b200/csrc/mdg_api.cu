@@ -392,8 +392,9 @@ static int step_impl(const MdgParams* P, const MdgReward* R, const MdgState* S, 
   if (!S->folds) return set_err(MDG_E_INVALID, "state.folds is null");
   if (L->window < 1 || L->head < 0 || L->head >= L->window) return set_err(MDG_E_INVALID, "bad window/head");
   if (L->mode < MDG_MODE_HOLD || L->mode > MDG_MODE_SINGLE) return set_err(MDG_E_INVALID, "bad mode");
-  const bool by_actions = L->mode == MDG_MODE_MULTI && IO->actions;
-  if (L->mode != MDG_MODE_HOLD && !IO->units && !by_actions) return set_err(MDG_E_INVALID, "units is null");
+  const bool by_weights = L->mode == MDG_MODE_MULTI && IO->weights;
+  const bool by_actions = L->mode == MDG_MODE_MULTI && IO->actions && !by_weights;
+  if (L->mode != MDG_MODE_HOLD && !IO->units && !by_actions && !by_weights) return set_err(MDG_E_INVALID, "units is null");
   if (by_actions && (L->action_atoms < 1 || L->action_atoms > 127))
     return set_err(MDG_E_INVALID, "action_atoms must be in [1, 127] with io.actions");
   if (L->mode == MDG_MODE_SINGLE && (L->asset_idx < 0 || L->asset_idx >= P->n_assets))
@@ -516,7 +517,7 @@ extern "C" int mdg_step_autoreset(const MdgParams* P, const MdgReward* R, const 
   if (L->n_envs == 0) return MDG_OK;
   ResetWsArgs a;
   MdgStepIO io = *IO;  // the reset draws from Philox (no injected stream) and takes no units
-  io.units = nullptr; io.normals = nullptr; io.uniforms = nullptr; io.actions = nullptr;
+  io.units = nullptr; io.normals = nullptr; io.uniforms = nullptr; io.actions = nullptr; io.weights = nullptr;
   rc = fill_ws_args(a, P, S, &io, L, fill_ticks, clear_nstep, workspace, workspace_bytes);
   if (rc) return rc;
   rc = step_impl(P, R, S, IO, L, a.count, a.list);  // the step kernel appends the finished envs to the list

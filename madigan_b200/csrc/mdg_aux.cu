@@ -9,6 +9,8 @@
 
 #include <stdlib.h>
 
+#include <cuda.h>  // CUtensorMap and its enums (types only: the driver entry point is looked up at run time)
+
 #include "mdg_common.cuh"
 
 namespace mdg {
@@ -322,6 +324,282 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// window materialiser, TMA variant (sm_90+/sm_100a): the common case -- StackerDiscrete's price window, (N, k, F)
+// layout, every normaliser but `expanding` -- as a tile-movement kernel.
+//
+//   load   the ring is a 2-D tensor [k*F rows][N envs] of fp64; a tile is 8 consecutive envs.  One elected thread
+//          issues one `cp.async.bulk.tensor.2d` per window row-group (box = F rows x 8 envs = F x 64 bytes) against an
+//          mbarrier: the whole tile (64 KB at 64 x 16) is in flight at once with no registers and no issue slots
+//          spent on it, and lands as T[row = s*F + f][env] in LOGICAL time order (the ring wrap is resolved by the
+//          box coordinates).
+//   patch  rows older than an env's last reset are replaced from the env-major prefix buffer (contiguous per env).
+//   math   one thread per (env, feature, half-column): lane = env fastest, so the column reads are at most 2-way
+//          bank-conflicted without padding or swizzle.
+//   store  fp32: the block's windows are staged as O[env][k*F] (env stride + 16 bytes: conflict-free) and written
+//          with one `cp.async.bulk.global.shared::cta` per env (4 KB contiguous); fp64: 32-byte pieces, direct.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// tile = E consecutive envs x FT consecutive features (a.envs, a.sstride carry E and FT; blockIdx.x = env tile * nq +
+// feature group, so that the feature groups of one env tile run together and their partial lines merge in L2)
+__global__ void window_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WindowArgs a) {
+  extern __shared__ __align__(128) unsigned char wsm[];
+  const int nv = a.n_valid, F = a.F, k = a.k, E = a.envs, FT = a.sstride;
+  const int nq = F / FT;
+  const int f0 = (int)(blockIdx.x % nq) * FT;
+  const int64_t e0 = (int64_t)(blockIdx.x / nq) * E;
+  const int rows = nv * FT;
+  double* T = reinterpret_cast<double*>(wsm);                                   // [rows][E]
+  unsigned char* O = wsm + (size_t)rows * E * sizeof(double);                  // [E][ostride] (fp32 staging)
+  const int ostride = a.estride;                                                // bytes per env in O (0: no staging)
+  double* cpar = reinterpret_cast<double*>(O + (size_t)E * ostride);            // [E*FT][2] (shift, scale)
+  int* s_since = reinterpret_cast<int*>(cpar + E * FT * 2);                     // [E]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_since + E);                    // 8-byte aligned by construction
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  int slot0 = (a.head - (nv - 1)) % k;
+  if (slot0 < 0) slot0 += k;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)),
+                 "r"((uint32_t)(rows * E * sizeof(double)))
+                 : "memory");
+    const uint64_t desc = reinterpret_cast<uint64_t>(&tmap);
+    for (int s = 0; s < nv; ++s) {
+      int slot = slot0 + s;
+      if (slot >= k) slot -= k;
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+              "r"(smem_u32(T + (size_t)s * FT * E)),
+          "l"(desc), "r"(smem_u32(mbar)), "r"((int)e0), "r"(slot * F + f0)
+          : "memory");
+    }
+  }
+  // rows written to the ring since each env's last reset (the newest row always is one)
+  if (tid < E) {
+    long long since = 0x7fffffff;
+    const int64_t e = e0 + tid;
+    if (a.timestamp && e < a.N) since = a.timestamp[e] - a.reset_ts[e] + 1;
+    s_since[tid] = since > nv ? nv : (int)since;
+  }
+  {  // wait for the tile (phase 0); a tile that never lands is a bug, not a hang
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(mbar))
+          : "memory");
+      if (spin > (1u << 24)) __trap();
+    }
+  }
+  __syncthreads();  // s_since visible
+  // patch: window rows s < nv - since of env e come from the prefix buffer (contiguous there) or are flat.
+  // Per patched env, every thread keeps up to four independent loads in flight (the run is contiguous in the prefix
+  // buffer when the tile holds all features).
+#pragma unroll 1
+  for (int el = 0; el < E; ++el) {
+    const int isince = s_since[el];
+    const int64_t e = e0 + el;
+    if (isince >= nv || e >= a.N) continue;
+    const int cnt = (nv - isince) * FT;
+    const double* pb = a.prefix ? a.prefix + ((int64_t)e * k + (k - 1 + isince - nv)) * F + f0 : nullptr;
+    constexpr int U = 4;
+    for (int r0 = tid; r0 < cnt; r0 += nthr * U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * nthr;
+        v[u] = 0.;
+        if (r < cnt) {
+          if (FT == F) {
+            v[u] = pb ? pb[r] : ((r % F == 0) ? 1. : 0.);
+          } else {
+            const int s = r / FT, f_ = r - s * FT;
+            v[u] = pb ? pb[s * F + f_] : ((f0 + f_ == 0) ? 1. : 0.);  // flat portfolio: ledgerNormedFull == [1, 0, ..., 0]
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * nthr;
+        if (r < cnt) T[(size_t)r * E + el] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+
+  // math: thread (e, f, z), env fastest; column = T + f*E + e, stride between samples FT*E
+  const int el = tid & (E - 1), f = (tid / E) % FT, z = tid / (E * FT), Z = nthr / (E * FT);
+  const int SS = FT * E;
+  double* col = T + f * E + el;
+  const bool live = (e0 + el) < a.N;
+  if (live && (a.norm == MDG_NORM_LOG || a.norm == MDG_NORM_LOG_STANDARD)) {
+    for (int s = z; s < nv; s += Z) {
+      double x = col[s * SS];
+      if (a.norm == MDG_NORM_LOG) x = (x != x) ? x : (x < 1e-5 ? 1e-5 : x);  // log(max(x, 1e-5))
+      col[s * SS] = fast_log(x);
+    }
+  }
+  if (a.norm == MDG_NORM_LOG_STANDARD) __syncthreads();
+  double* cp = cpar + (el * FT + f) * 2;
+  if (live && z == 0) {
+    double shift = 0., scale = 1.;
+    const bool pw = (F == 1);
+    switch (a.norm) {
+      case MDG_NORM_LOOKBACK:
+      case MDG_NORM_LOOKBACK_LOG:
+        scale = 1. / col[(nv - 1) * SS];
+        break;
+      case MDG_NORM_STANDARD:
+        shift = col_sum<0>(col, nv, SS, 0., pw) / nv;
+        scale = 1. / sqrt(col_sum<1>(col, nv, SS, shift, pw) / nv);
+        break;
+      case MDG_NORM_LOG_STANDARD: {
+        int cnt = 0;
+        for (int s = 0; s < nv; ++s) cnt += (col[s * SS] == col[s * SS]) ? 1 : 0;
+        shift = col_sum<2>(col, nv, SS, 0., pw) / cnt;
+        scale = 1. / sqrt(col_sum<3>(col, nv, SS, shift, pw) / cnt);
+        break;
+      }
+      default:
+        break;
+    }
+    cp[0] = shift; cp[1] = scale;
+  }
+  __syncthreads();
+  const bool scaled = a.norm == MDG_NORM_LOOKBACK || a.norm == MDG_NORM_LOOKBACK_LOG ||
+                      a.norm == MDG_NORM_STANDARD || a.norm == MDG_NORM_LOG_STANDARD;
+  const bool zs = a.norm == MDG_NORM_STANDARD || a.norm == MDG_NORM_LOG_STANDARD;
+  const bool f32 = a.out_dtype == MDG_DTYPE_F32;
+  if (live) {
+    const double shift = cp[0], scale = cp[1];
+    float* orow = reinterpret_cast<float*>(O + (size_t)el * ostride);
+    for (int s = z; s < nv; s += Z) {
+      double x = col[s * SS];
+      if (scaled) {
+        if (zs) {
+          x = nan_to_num((x - shift) * scale);
+        } else {
+          x = x * scale;
+          if (a.norm == MDG_NORM_LOOKBACK_LOG) x = fast_log(x);
+        }
+      }
+      if (f32) orow[s * FT + f] = (float)x; else col[s * SS] = x;
+    }
+  }
+  if (f32 && FT == F) {  // whole windows: one bulk store per env
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes of O -> visible to the bulk copy
+    __syncthreads();
+    if (tid < E && (e0 + tid) < a.N) {
+      const uint32_t bytes = (uint32_t)(rows * sizeof(float));
+      float* dst = reinterpret_cast<float*>(a.out) + (e0 + tid) * rows;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                   "r"(smem_u32(O + (size_t)tid * ostride)), "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may go away after this
+    }
+  } else if (f32) {  // a feature group: FT consecutive fp32 per (env, sample), linear reads of O
+    __syncthreads();
+    float* out = reinterpret_cast<float*>(a.out);
+    for (int el_ = 0; el_ < E; ++el_) {
+      if (e0 + el_ >= a.N) break;
+      const float* orow = reinterpret_cast<const float*>(O + (size_t)el_ * ostride);
+      float* dst = out + (e0 + el_) * (int64_t)nv * F + f0;
+      for (int r = tid; r < rows; r += nthr) {
+        const int s = r / FT, f_ = r - s * FT;
+        dst[s * F + f_] = orow[r];
+      }
+    }
+  } else {
+    __syncthreads();
+    double* out = reinterpret_cast<double*>(a.out);
+    const int per = 32 / E > 0 ? 32 / E : 1;  // consecutive elements of one env handled by one warp
+    (void)per;
+    for (int idx = tid; idx < rows * E; idx += nthr) {  // lanes: env fastest
+      const int e_ = idx & (E - 1), r = idx / E;
+      const int s = r / FT, f_ = r - s * FT;
+      if (e0 + e_ < a.N) out[((e0 + e_) * (int64_t)nv + s) * F + f0 + f_] = T[(size_t)r * E + e_];
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static const EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// launch the TMA variant when the case qualifies; returns 1 when it did, 0 when the caller should fall back, <0 on error
+static int launch_window_tma(const MdgWindow* w, WindowArgs a) {
+  // OPT-IN (MDG_WIN_TMA=1): measured on B200 at 65,536 x 64 x 16 -> fp32 the TMA tile kernel takes 423 us (None) /
+  // 512 us (standard_normal) against 232 / 351 us for the register-staged kernel below (profiles/r2_notes.md): the
+  // ring is env-minor, so a tile of 8 envs is 1,024 rows of 64 bytes for the TMA engine, and 18 % of the envs need
+  // their pre-reset rows patched in afterwards.  Parity-tested either way (tests/test_gpu_window.py).
+  static const int enabled = [] { const char* v = getenv("MDG_WIN_TMA"); return v ? atoi(v) : 0; }();
+  static const int env_E = [] { const char* v = getenv("MDG_WIN_TMA_E"); return v ? atoi(v) : 8; }();
+  static const int env_FT = [] { const char* v = getenv("MDG_WIN_TMA_FT"); return v ? atoi(v) : 16; }();
+  if (!enabled) return 0;
+  const int F = a.F, nv = a.n_valid;
+  if (a.xform != MDG_XFORM_NONE || a.layout != MDG_LAYOUT_NKF || a.norm == MDG_NORM_EXPANDING) return 0;
+  int E = env_E, FT = env_FT;
+  if (E != 8 && E != 16 && E != 32) return 0;
+  if (FT > F) FT = F;
+  if (F % FT) return 0;
+  if ((a.N & 1) || a.N < E || (reinterpret_cast<uintptr_t>(a.ring) & 15)) return 0;
+  if (((size_t)FT * E * sizeof(double)) % 128) return 0;  // every box lands on a 128-byte boundary
+  const bool f32 = a.out_dtype == MDG_DTYPE_F32;
+  const size_t rows = (size_t)nv * FT;
+  if (f32 && FT == F && (((rows * sizeof(float)) & 15) || (reinterpret_cast<uintptr_t>(a.out) & 15))) return 0;
+  const int ostride = f32 ? (int)(rows * sizeof(float) + 16) : 0;
+  const size_t smem = rows * E * sizeof(double) + (size_t)E * ostride + (size_t)E * FT * 2 * sizeof(double) +
+                      E * sizeof(int) + 16;
+  if (smem > 110 * 1024) return 0;
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return 0;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a.N, (cuuint64_t)a.k * (cuuint64_t)F};
+  const cuuint64_t gstride[1] = {(cuuint64_t)a.N * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)E, (cuuint32_t)FT};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(a.ring), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return 0;
+  static size_t smem_allowed = 48 * 1024;
+  if (smem > smem_allowed) {
+    cudaError_t ce = cudaFuncSetAttribute(window_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return cuda_err(ce, "window (tma) smem attr");
+    smem_allowed = smem;
+  }
+  a.estride = ostride;
+  a.envs = E;
+  a.sstride = FT;
+  int Z = 256 / (E * FT);
+  if (Z < 1) Z = 1;
+  const unsigned grid = (unsigned)(((a.N + E - 1) / E) * (F / FT));
+  window_tma_kernel<<<grid, E * FT * Z, smem, (cudaStream_t)w->stream>>>(tmap, a);
+  const int rc = cuda_err(cudaGetLastError(), "mdg_materialise_window (tma) launch");
+  return rc ? rc : 1;
+}
+
 __global__ void time_kernel(const int64_t* timestamp, int64_t N, int nv, int64_t* out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * nv) return;
@@ -466,6 +744,10 @@ extern "C" int mdg_materialise_window(const MdgWindow* w) {
   a.ring = w->ring; a.prefix = w->prefix; a.timestamp = w->timestamp; a.reset_ts = w->reset_ts;
   a.out = w->out; a.N = w->n_envs; a.F = n_feats; a.k = window; a.head = head; a.n_valid = n_valid;
   a.norm = w->norm_type; a.out_dtype = w->out_dtype; a.layout = w->out_layout; a.flat_prefix = w->flat_prefix;
+  {
+    const int t = launch_window_tma(w, a);
+    if (t != 0) return t < 0 ? t : MDG_OK;
+  }
   // envs per block: a power of two with about 64 columns per block and two threads per column -- small tiles
   // (35 KB at 64 x 16), six blocks per SM: measured best at 65,536 x 64 x 16 (profiles/window_cost.py)
   int envs = 32;

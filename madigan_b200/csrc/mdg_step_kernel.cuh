@@ -397,6 +397,15 @@ __device__ __forceinline__ double action_units(int act, int half, double scale, 
   return (double)(act - half) * (scale / price);
 }
 
+// ddpg.py:182-207: target weights -> units.  desired = w / sum(w) in fp32 (what torch computes on the actor's
+// output), widened; units = ((desired - ledgerNormedFull_i) * equity) / price, ledgerNormedFull_i =
+// (ledger_i * price_i) / equity (Portfolio.cpp:150-155).  w_sum == 0: the weights are taken as they are (:193-194).
+__device__ __forceinline__ double weight_units(float w, float w_sum, double price, double cur, double equity) {
+  const float d = (w_sum == 0.f) ? w : w / w_sum;
+  const double cur_w = (cur * price) / equity;
+  return (((double)d - cur_w) * equity) / price;
+}
+
 // after the tick of asset i: state/observation stores, fold of the new position value, reward stash
 template <bool PAIRS, int BS>
 __device__ __forceinline__ void post_tick(const StepArgs& a, StepAcc& A, int64_t N, int64_t e, int na, int i,
@@ -529,6 +538,13 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   const int8_t* arow = (ACTIONS && mode == MDG_MODE_MULTI && a.IO.actions) ? a.IO.actions + e * na : nullptr;
   const double act_scale = arow ? a.L.unit_size * (((A.cash + A.rSE) + (A.rAV - A.rML)) / P.required_margin) : 0.;
   const int act_half = a.L.action_atoms / 2;
+  // DDPG.action_to_transaction (ddpg.py:182-207), likewise: target weights (cash first) -> units
+  const float* wrow = (ACTIONS && mode == MDG_MODE_MULTI && a.IO.weights) ? a.IO.weights + e * (na + 1) : nullptr;
+  float w_sum = 0.f;
+  if (wrow) {
+    w_sum = wrow[0];
+    for (int j = 1; j <= na; ++j) w_sum = w_sum + wrow[j];
+  }
 
   StepConsts c;
   c.reqM = P.required_margin;
@@ -576,10 +592,13 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
         const double2 u2 = __ldcg(reinterpret_cast<const double2*>(urow + 2 * p));
         units[0] = u2.x; units[1] = u2.y;
       } else {
-        units[0] = (mode == MDG_MODE_MULTI && !arow) ? urow[2 * p] : 0.;
-        units[1] = (mode == MDG_MODE_MULTI && !arow) ? urow[2 * p + 1] : 0.;
+        units[0] = (mode == MDG_MODE_MULTI && !arow && !wrow) ? urow[2 * p] : 0.;
+        units[1] = (mode == MDG_MODE_MULTI && !arow && !wrow) ? urow[2 * p + 1] : 0.;
       }
-      if (arow) {
+      if (wrow) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) units[q] = weight_units(wrow[2 * p + q + 1], w_sum, price[q], cur[q], prevEq);
+      } else if (arow) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) units[q] = action_units(arow[2 * p + q], act_half, act_scale, price[q], cur[q]);
       }
@@ -627,7 +646,8 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       double mep = S.mean_entry[(int64_t)i * N + e];
       double bm = S.borrowed[(int64_t)i * N + e];
       double units = 0.;
-      if (arow) units = action_units(arow[i], act_half, act_scale, price, cur);
+      if (wrow) units = weight_units(wrow[i + 1], w_sum, price, cur, prevEq);
+      else if (arow) units = action_units(arow[i], act_half, act_scale, price, cur);
       else if (mode == MDG_MODE_MULTI) units = urow[i];
       else if (mode == MDG_MODE_SINGLE && i == a.L.asset_idx) units = urow[0];
       double tp, tu, tc, prev_val;
@@ -818,7 +838,7 @@ static inline int launch_step(StepArgs& a) {
   const unsigned grid = (unsigned)((N + 127) / 128);
   a.units_v2 = (a.IO.units && (reinterpret_cast<uintptr_t>(a.IO.units) & 15) == 0 && a.P.n_assets % 2 == 0) ? 1 : 0;
   const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
-  const bool acts = a.L.mode == MDG_MODE_MULTI && a.IO.actions;
+  const bool acts = a.L.mode == MDG_MODE_MULTI && (a.IO.actions || a.IO.weights);
   const bool small = N <= 148 * 512 * 2;  // up to two waves at 4 blocks per SM
 #define MDG_LAUNCH(PAIRS_, MINB_, ACT_) step_kernel<PAIRS_, 128, MINB_, ACT_><<<grid, 128, smem, st>>>(a)
   if (small) {

@@ -209,7 +209,9 @@ class Env:
 
     def _copy_ctx(self):
         """`with` context for torch ops that must run on this env's stream (staging copies)."""
-        return _NULL_CTX if self._stream is None else torch.cuda.stream(self._stream)
+        if self._stream is None or _raw_stream(self.device.index) == self._stream_ptr:
+            return _NULL_CTX  # torch's current stream already is the env's stream
+        return torch.cuda.stream(self._stream)
 
     def bind_stream(self, stream):
         """Pin this env's launches to ``stream`` (a torch.cuda.Stream; None = torch's current stream again).
@@ -422,6 +424,62 @@ class Env:
         t = self.t
         return self._state(), t["reward"], t["done"], self._info
 
+    def step_weights(self, weights, *, normals=None, uniforms=None, auto_reset=False):
+        """``env.step(agent.action_to_transaction(weights))`` in one launch for a DDPG-style actor: ``weights`` is an
+        (N, nA+1) real tensor of target portfolio weights, cash first; the kernel converts them to transaction units
+        exactly as ``DDPG.action_to_transaction`` does (modelling/algorithm/ddpg.py:182-207 -- ``desired = w / w.sum()``
+        in fp32, ``units = (desired - ledgerNormedFull)[1:] * equity / currentPrices``) and steps.  4 bytes per weight
+        cross to the device instead of 8 per unit.  Returns what ``step(units)`` returns."""
+        io = self._IO
+        with self._device_ctx():
+            w = weights if isinstance(weights, torch.Tensor) else torch.as_tensor(weights)
+            if w.dtype != torch.float32:
+                w = w.to(torch.float32)
+            want = torch.Size((self.N, self.nA + 1))
+            if w.shape != want:
+                if self.N == 1 and w.dim() == 1:
+                    w = w.unsqueeze(0)
+                if w.shape != want:
+                    raise ValueError(f"weights must have shape {tuple(want)}, got {tuple(w.shape)}")
+            if not w.is_cuda or w.device != self.device or not w.is_contiguous():
+                if "weights" not in self.t:
+                    self.t["weights"] = torch.empty((self.N, self.nA + 1), dtype=torch.float32, device=self.device)
+                with self._copy_ctx():
+                    self.t["weights"].copy_(w, non_blocking=True)
+                w = self.t["weights"]
+            io.units = None
+            io.weights = w.data_ptr()
+            try:
+                if normals is None and uniforms is None:
+                    io.normals = io.uniforms = None
+                    keep = None
+                else:
+                    io.normals, io.uniforms, keep = self._noise(normals, uniforms)
+                head0 = self.head
+                self.head = (self.head + 1) % self.k
+                L = self._launch(A.MODE_MULTI, 0)
+                self.head = head0
+                if auto_reset and keep is None:
+                    ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr, self._stream)
+                    check(self._lib.mdg_step_autoreset(self._pP, self._pR, self._pS, self._pIO, self._pL, self.k, 1,
+                                                       ws.data_ptr(), ws.numel()))
+                    self.launches += 1  # + the refill kernel
+                    auto_reset = False
+                else:
+                    check(self._lib.mdg_step(self._pP, self._pR, self._pS, self._pIO, self._pL))
+            finally:
+                io.weights = None
+            self.head = L.head
+            self.n_valid = min(self.k, self.n_valid + 1)
+            self.launches += 1
+            if self.R.shaper != A.SHAPER_OFF:
+                self._gstep += 1
+            self._version += 1
+            if auto_reset:
+                self._reset_launch(self.t["done"], self.k, True, None, None)
+        t = self.t
+        return self._state(), t["reward"], t["done"], self._info
+
     # ------------------------------------------------------------------ in-kernel rewards
     @property
     def agent_reward(self):
@@ -619,7 +677,7 @@ class Env:
         self.launches += 2
         return out
 
-    _STAGING = ("units", "actions")  # host-input staging buffers: not state
+    _STAGING = ("units", "actions", "weights")  # host-input staging buffers: not state
 
     def state_dict(self):
         """Checkpoint of the env (the reference cannot checkpoint its env: wall-clock seeded RNG)."""

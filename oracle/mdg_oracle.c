@@ -766,6 +766,23 @@ void orc_action_units(const OrcEnv *e, const int8_t *actions, int action_atoms, 
   }
 }
 
+/* DDPG.action_to_transaction, modelling/algorithm/ddpg.py:182-207: units from target weights (cash first).
+ * desired = w / w.sum() in fp32 (torch on the actor's fp32 output; :193-196), widened by the subtraction with the
+ * fp64 ledgerNormedFull (:198-201); units = amounts[1:] / currentPrices (:205). */
+void orc_weight_units(const OrcEnv *e, const float *w, double *units) {
+  const int nA = e->P.n_assets;
+  double cur[MDG_MAX_ASSETS + 1];
+  float s = w[0];
+  for (int j = 1; j <= nA; ++j) s = s + w[j];
+  orc_ledger_normed_full(e, cur);
+  const double eq = orc_equity(e);
+  for (int j = 0; j < nA; ++j) {
+    const float d = (s == 0.f) ? w[j + 1] : w[j + 1] / s;
+    const double amount = ((double)d - cur[j + 1]) * eq;
+    units[j] = amount / e->price[j];
+  }
+}
+
 void orc_batch_step(OrcBatch *b, const MdgStepIO *io, const MdgLaunch *L, int threads) {
   const int64_t N = b->n;
   (void)threads;
@@ -777,7 +794,9 @@ void orc_batch_step(OrcBatch *b, const MdgStepIO *io, const MdgLaunch *L, int th
     const double *pn = 0, *pu = 0;
     if (io->normals) { for (int s = 0; s < e->P.n_normals; ++s) nz[s] = io->normals[s * N + i]; pn = nz; }
     if (io->uniforms) { for (int s = 0; s < e->P.n_uniforms; ++s) uz[s] = io->uniforms[s * N + i]; pu = uz; }
-    if (L->mode == MDG_MODE_MULTI && io->actions)
+    if (L->mode == MDG_MODE_MULTI && io->weights)
+      orc_weight_units(e, io->weights + i * (nA + 1), un);
+    else if (L->mode == MDG_MODE_MULTI && io->actions)
       orc_action_units(e, io->actions + i * nA, L->action_atoms, L->unit_size, un);
     else if (L->mode == MDG_MODE_MULTI) for (int j = 0; j < nA; ++j) un[j] = io->units[i * nA + j];
     if (L->mode == MDG_MODE_SINGLE) un[0] = io->units[i];

@@ -94,6 +94,7 @@ OrcEnv *orc_batch_env(OrcBatch *b, int64_t i);
 void orc_batch_export_state(const OrcBatch *b, const MdgState *host_state);
 /* same argument meaning as mdg_step / mdg_reset, but every pointer is a HOST pointer */
 void orc_action_units(const OrcEnv *e, const int8_t *actions, int action_atoms, double unit_size, double *units);
+void orc_weight_units(const OrcEnv *e, const float *weights, double *units);
 void orc_batch_step(OrcBatch *b, const MdgStepIO *io, const MdgLaunch *launch, int threads);
 void orc_batch_reset(OrcBatch *b, const MdgStepIO *io, const MdgLaunch *launch,
                      const uint8_t *mask, int fill_ticks, int clear_nstep, int threads);

@@ -89,6 +89,8 @@ def lib():
         L.orc_draw_uniform.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int]
         L.orc_draw_uniform.restype = dbl
         L.orc_action_units.argtypes = [pe, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.orc_weight_units.argtypes = [pe, C.c_void_p, C.c_void_p]
+        L.orc_weight_units.restype = None
         L.orc_batch_create.argtypes = [C.c_int64, C.POINTER(A.MdgParams), C.POINTER(A.MdgReward), C.c_uint64, C.c_int64]
         L.orc_batch_create.restype = C.c_void_p
         L.orc_batch_destroy.argtypes = [C.c_void_p]
@@ -188,6 +190,13 @@ class OracleEnv:
         out = np.zeros(self.nA)
         self.L.orc_action_units(C.byref(self.e), a.ctypes.data_as(C.c_void_p), int(action_atoms), float(unit_size),
                                 out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def weight_units(self, weights):
+        """DDPG.action_to_transaction (ddpg.py:182-207) on the current portfolio: fp32 target weights (cash first) -> units"""
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        out = np.zeros(self.nA)
+        self.L.orc_weight_units(C.byref(self.e), w.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         return out
 
     def handleTransaction(self, i, price, units, cost=0.):
@@ -332,6 +341,16 @@ class OracleBatch:
         L = self._launch(A.MODE_MULTI)
         L.action_atoms, L.unit_size = int(action_atoms), float(unit_size)
         self.L.orc_batch_step(self.h, C.byref(io), C.byref(L), self.threads)
+
+    def step_weights(self, weights, normals=None, uniforms=None):
+        """weights: (N,nA+1) fp32 target weights -> units as DDPG.action_to_transaction (ddpg.py:182-207), then step."""
+        self.head = (self.head + 1) % self.k
+        self.n_valid = min(self.k, self.n_valid + 1)
+        io = self._io(None, normals, uniforms)
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        self._keep.append(w)
+        io.weights = w.ctypes.data_as(C.c_void_p)
+        self.L.orc_batch_step(self.h, C.byref(io), C.byref(self._launch(A.MODE_MULTI)), self.threads)
 
     def state(self):
         N, nA = self.N, self.nA
