@@ -553,9 +553,12 @@ static int launch_window_tma(const MdgWindow* w, WindowArgs a) {
   // 512 us (standard_normal) against 232 / 351 us for the register-staged kernel below (profiles/r2_notes.md): the
   // ring is env-minor, so a tile of 8 envs is 1,024 rows of 64 bytes for the TMA engine, and 18 % of the envs need
   // their pre-reset rows patched in afterwards.  Parity-tested either way (tests/test_gpu_window.py).
-  static const int enabled = [] { const char* v = getenv("MDG_WIN_TMA"); return v ? atoi(v) : 0; }();
-  static const int env_E = [] { const char* v = getenv("MDG_WIN_TMA_E"); return v ? atoi(v) : 8; }();
-  static const int env_FT = [] { const char* v = getenv("MDG_WIN_TMA_FT"); return v ? atoi(v) : 16; }();
+  const char* en = getenv("MDG_WIN_TMA");  // read per call: the parity tests switch it on and off in one process
+  const int enabled = en ? atoi(en) : 0;
+  if (!enabled) return 0;
+  const char* vE = getenv("MDG_WIN_TMA_E");
+  const char* vF = getenv("MDG_WIN_TMA_FT");
+  const int env_E = vE ? atoi(vE) : 8, env_FT = vF ? atoi(vF) : 16;
   if (!enabled) return 0;
   const int F = a.F, nv = a.n_valid;
   if (a.xform != MDG_XFORM_NONE || a.layout != MDG_LAYOUT_NKF || a.norm == MDG_NORM_EXPANDING) return 0;

@@ -72,6 +72,46 @@ def test_window_matches_numpy_random(norm, nF, k, N):
     np.testing.assert_allclose(got_p, ref_p, rtol=1e-9, atol=1e-11, equal_nan=True)
 
 
+@pytest.mark.parametrize("norm", [n for n in NORMS if n != "expanding"])
+@pytest.mark.parametrize("nF,k,N,E,FT", [(16, 64, 300, 8, 16), (16, 64, 4098, 32, 4), (2, 64, 334, 16, 2), (16, 7, 34, 8, 16)])
+def test_window_tma_variant_matches_numpy_and_register_path(monkeypatch, norm, nF, k, N, E, FT):
+    """The opt-in TMA tile kernel (cp.async.bulk.tensor loads against an mbarrier, bulk stores; csrc/mdg_aux.cu
+    window_tma_kernel) against numpy and against the default register-staged kernel, incl. rows older than a reset
+    that come from the prefix buffer."""
+    rng = np.random.default_rng(nF * 10 + k)
+    env = make_env(N, nF, k)
+    R = k + 5
+    rows = np.abs(10 + np.cumsum(rng.standard_normal((R, nF, N)) * .2, axis=0)) + .1
+    load_ring(env, rows, R - 1)
+    ref = py_oracle.normalise_batch(rows[R - k:].transpose(2, 0, 1), norm)
+    monkeypatch.setenv("MDG_WIN_TMA_E", str(E))
+    monkeypatch.setenv("MDG_WIN_TMA_FT", str(FT))
+    for dtype, tol in ((torch.float64, dict(rtol=1e-9, atol=1e-11)), (torch.float32, dict(rtol=2e-6, atol=1e-6))):
+        monkeypatch.setenv("MDG_WIN_TMA", "1")
+        got = env.window(norm, dtype=dtype).cpu().numpy()
+        monkeypatch.setenv("MDG_WIN_TMA", "0")
+        base = env.window(norm, dtype=dtype).cpu().numpy()
+        np.testing.assert_allclose(got, ref.astype(got.dtype), equal_nan=True, **tol)
+        np.testing.assert_array_equal(got, base)
+    # after real steps and resets: pre-reset rows come from the prefix buffer; both kernels must agree bit for bit
+    from madigan_b200.environments import Env
+    env2 = Env("OU", 1e6, {"data_source_config": {"mean": [10.] * 4, "theta": [.1] * 4, "phi": [.05] * 4}}, n_envs=258,
+               window=16, seed=3, device="cuda")
+    env2.reset(fill_history=True)
+    u = torch.zeros((258, 4), dtype=torch.float64, device="cuda")
+    for t in range(9):
+        env2.step(u)
+        if t == 4:
+            m = torch.zeros(258, dtype=torch.bool, device="cuda"); m[::3] = True
+            env2.reset(mask=m, fill_history=True)
+    monkeypatch.setenv("MDG_WIN_TMA_E", "8"); monkeypatch.setenv("MDG_WIN_TMA_FT", "4")
+    monkeypatch.setenv("MDG_WIN_TMA", "1")
+    a_ = env2.window(norm, dtype=torch.float64).cpu().numpy()
+    monkeypatch.setenv("MDG_WIN_TMA", "0")
+    b_ = env2.window(norm, dtype=torch.float64).cpu().numpy()
+    np.testing.assert_array_equal(a_, b_)
+
+
 def test_stacker_discrete_api_roundtrip():
     """The reference's agent loop (offpolicy_q.py:93-99): reset -> stream_state -> initialize_history -> current_data."""
     from madigan_b200.environments import Env
