@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 9
+#define MDG_ABI_VERSION 11
 #define MDG_MAX_ASSETS 16
 #define MDG_GEN_NPARAM 10
 #define MDG_MAX_NSTEP 64
@@ -239,7 +239,8 @@ enum MdgNorm {
 
 int mdg_abi_version(void);
 /* sizeof of the ABI structs as compiled: 0 MdgAssetGen 1 MdgParams 2 MdgReward 3 MdgState 4 MdgStepIO
- * 5 MdgLaunch 6 MdgDerived 7 MdgWindow 8 MdgReplay 9 MdgReplayBatch 10 MdgRewardNorm; -1 for an unknown index (lets a binding verify its struct mirror) */
+ * 5 MdgLaunch 6 MdgDerived 7 MdgWindow 8 MdgReplay 9 MdgReplayBatch 10 MdgRewardNorm 11 MdgTearsheet; -1 for an unknown
+ * index (lets a binding verify its struct mirror) */
 int mdg_sizeof(int which);
 const char *mdg_last_error(void);
 
@@ -305,6 +306,12 @@ typedef struct MdgWindow {
   void *out;                 /* (N, n_valid, F_out) or (N, F_out, n_valid)                    */
   void *stream;
   int32_t transform;         /* MDG_XFORM_*: the other price stackers of utils/preprocessor.py */
+  int32_t stride;            /* MultiStackerDiscrete (preprocessor.py:202-288): window row s is the ring row of age
+                                age0 + (n_valid-1-s) * stride; 0 or 1 = every row                                */
+  int32_t age0;              /* age of the newest window row (0 = the newest ring row)                          */
+  int32_t out_feats_total;   /* > 0: `out` has this many features per row and this window goes to columns
+                                [out_feat_offset, out_feat_offset + F_out) -- the concatenation over dilations  */
+  int32_t out_feat_offset;
   int32_t _pad;
 } MdgWindow;
 #define MDG_XFORM_NONE 0       /* StackerDiscrete            preprocessor.py:143-199, F_out = F            */
@@ -403,6 +410,41 @@ int mdg_reward_norm_reset(const MdgRewardNorm *rn, const uint8_t *mask, void *st
  * "needs to be called when environment resets / episode ends" (reward_normalization.pyx:84) */
 int mdg_reward_norm_stream(const MdgRewardNorm *rn, const double *reward, const uint8_t *reset_mask, double *out,
                            void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * On-device episode tearsheet (utils/metrics.py:83-171 test_summary and its helpers :334-421): the reference
+ * records every step of a test episode on the host (equity, reward, ledger, transaction costs) and reduces the
+ * lists with pandas at the end; here every env streams its episode into a handful of accumulators, one kernel per
+ * step, and one kernel turns them into the tearsheet fields.  An env accumulates while active[e] != 0; the step
+ * that reports done[e] is the last one recorded (the reference's `while not done` loop), then the env is frozen
+ * until mdg_tearsheet_reset re-arms it.  Call mdg_tearsheet_update AFTER the step and BEFORE the env is reset.
+ * Returns are log returns of the equity curve at offsets 2^j steps, j < n_offsets (metrics.py:71-78,367-411 with unit
+ * timestamps); std by Welford (the reference: two-pass numpy; results agree to ~1e-12).
+ * Every pointer is [N] unless noted. */
+#define MDG_TS_MAX_OFFSETS 8
+typedef struct MdgTearsheet {
+  int64_t n_envs;
+  int32_t n_assets;
+  int32_t n_offsets;       /* J: offsets 1, 2, 4, ..., 2^(J-1); eq_ring holds 2^(J-1) equities per env */
+  int64_t *nsteps;
+  uint8_t *active;
+  double *sum_equity, *last_equity, *sum_reward, *peak, *min_valley, *sum_cost;
+  double *in_pos;          /* [nA][N] steps with ledger != 0 */
+  double *eq_ring;         /* [2^(J-1)][N] */
+  int32_t *ret_n;          /* [J][N] valid returns */
+  double *ret_mean, *ret_m2, *ret_down; /* [J][N] Welford mean / M2, sum of squared negative returns */
+} MdgTearsheet;
+/* fields of mdg_tearsheet_summary's output, [MDG_TS_NFIXED + 3*J + nA][N]:
+ *   0 nsteps 1 mean_equity 2 final_equity 3 mean_reward 4 max_drawdown (min of equity / expanding max, metrics.py:413-421)
+ *   5 mean_transaction_cost (over steps x assets) 6 total_transaction_cost
+ *   7+3j equity_returns_offset_2^j (nanmean)  8+3j equity_sharpe_offset_2^j (:334-348)  9+3j equity_sortino_offset_2^j
+ *   (:350-365); NaN when 2^j > (nsteps-1)//10 (:108,133)
+ *   7+3J+a time_spent_in_pos_<asset a> (:116-122) */
+#define MDG_TS_NFIXED 7
+int mdg_tearsheet_reset(const MdgTearsheet *ts, const uint8_t *mask, void *stream);
+int mdg_tearsheet_update(const MdgParams *params, const MdgState *state, const MdgStepIO *io, const MdgTearsheet *ts,
+                         void *stream);
+int mdg_tearsheet_summary(const MdgTearsheet *ts, double *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ checks the struct sizes against the compiled library (``mdg_sizeof``).
 """
 import ctypes as C
 
-MDG_ABI_VERSION = 9
+MDG_ABI_VERSION = 11
 FLAG_FORCE_EXACT_GATE = 1
 XFORM_NONE, XFORM_PAIR_RATIO, XFORM_RETURNS = 0, 1, 2
 MDG_MAX_ASSETS = 16
@@ -109,6 +109,16 @@ class MdgReplayBatch(C.Structure):
 RN_NULL, RN_SHARPE_FIXED, RN_SORTINO_A, RN_SORTINO_B, RN_SORTINO_C, RN_SHARPE_EWMA = range(6)
 
 
+MDG_TS_MAX_OFFSETS = 8
+MDG_TS_NFIXED = 7
+
+
+class MdgTearsheet(C.Structure):
+    _fields_ = [("n_envs", C.c_int64), ("n_assets", C.c_int32), ("n_offsets", C.c_int32)] + \
+               [(n, _dp) for n in ("nsteps", "active", "sum_equity", "last_equity", "sum_reward", "peak", "min_valley",
+                                   "sum_cost", "in_pos", "eq_ring", "ret_n", "ret_mean", "ret_m2", "ret_down")]
+
+
 class MdgRewardNorm(C.Structure):
     _fields_ = [("kind", C.c_int32), ("window", C.c_int32), ("n_envs", C.c_int64), ("alpha", C.c_double)] + \
                [(n, _dp) for n in ("buffer", "size", "front", "count", "mean_est", "ssq", "ewma", "ewma_old",
@@ -140,6 +150,9 @@ SYMBOLS = {
                                     C.c_void_p]),
     "mdg_reward_norm_reset": (C.c_int, [_P(MdgRewardNorm), C.c_void_p, C.c_void_p]),
     "mdg_reward_norm_stream": (C.c_int, [_P(MdgRewardNorm), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mdg_tearsheet_reset": (C.c_int, [_P(MdgTearsheet), C.c_void_p, C.c_void_p]),
+    "mdg_tearsheet_update": (C.c_int, [_P(MdgParams), _P(MdgState), _P(MdgStepIO), _P(MdgTearsheet), C.c_void_p]),
+    "mdg_tearsheet_summary": (C.c_int, [_P(MdgTearsheet), C.c_void_p, C.c_void_p]),
 }
 
 
@@ -153,4 +166,4 @@ def bind(lib):
 
 
 STRUCTS = (MdgAssetGen, MdgParams, MdgReward, MdgState, MdgStepIO, MdgLaunch, MdgDerived, MdgWindow, MdgReplay,
-           MdgReplayBatch, MdgRewardNorm)  # mdg_sizeof order
+           MdgReplayBatch, MdgRewardNorm, MdgTearsheet)  # mdg_sizeof order

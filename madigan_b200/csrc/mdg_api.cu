@@ -566,6 +566,7 @@ extern "C" int mdg_sizeof(int which) {
     case 8: return (int)sizeof(MdgReplay);
     case 9: return (int)sizeof(MdgReplayBatch);
     case 10: return (int)sizeof(MdgRewardNorm);
+    case 11: return (int)sizeof(MdgTearsheet);
   }
   return -1;
 }

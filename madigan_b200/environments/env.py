@@ -303,11 +303,12 @@ class Env:
             self.n_valid = fill
         return self._state()
 
-    def step(self, *args, normals=None, uniforms=None, auto_reset=False):
+    def step(self, *args, normals=None, uniforms=None, auto_reset=False, tearsheet=None):
         """``step()`` hold (Env.h:189-204); ``step(units)`` with units (N,nA) (Env.h:206-230);
         ``step(assetIdx|assetCode, units)`` with units (N,) (Env.h:232-256, env.cpp:995-1005).
         Returns ``(State, reward (N,), done (N,) bool, EnvInfo)``; the tensors are views of live
-        buffers that the next call overwrites (same aliasing as the reference's Eigen maps)."""
+        buffers that the next call overwrites (same aliasing as the reference's Eigen maps).
+        ``tearsheet``: a ``utils.metrics.EpisodeTearsheet`` that records the step before any auto-reset."""
         asset_idx = 0
         if len(args) == 0:
             mode, units = A.MODE_HOLD, None
@@ -349,7 +350,7 @@ class Env:
             self.head = (self.head + 1) % self.k
             L = self._launch(mode, asset_idx)
             self.head = head0  # the ring head moves only once the launch has been accepted
-            if auto_reset and keep is None:  # step + masked reset + history fill in one trip through the binding
+            if auto_reset and keep is None and tearsheet is None:  # step + masked reset + history fill in one trip through the binding
                 ws = _reset_workspace(self._lib, self.P, self.N, self.k, self.device, self._stream_ptr, self._stream)
                 check(self._lib.mdg_step_autoreset(self._pP, self._pR, self._pS, self._pIO, self._pL, self.k, 1,
                                                    ws.data_ptr(), ws.numel()))
@@ -363,6 +364,8 @@ class Env:
             if mode != A.MODE_HOLD and self.R.shaper != A.SHAPER_OFF:
                 self._gstep += 1
             self._version += 1
+            if tearsheet is not None:
+                tearsheet.update()
             if auto_reset:
                 self._reset_launch(self.t["done"], self.k, True, None, None)
         t = self.t
