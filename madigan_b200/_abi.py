@@ -81,7 +81,8 @@ class MdgWindow(C.Structure):
     _fields_ = [("ring", _dp), ("prefix", _dp), ("timestamp", _dp), ("reset_ts", _dp), ("n_envs", C.c_int64),
                 ("n_feats", C.c_int32), ("window", C.c_int32), ("head", C.c_int32), ("n_valid", C.c_int32),
                 ("norm_type", C.c_int32), ("flat_prefix", C.c_int32), ("out_dtype", C.c_int32),
-                ("out_layout", C.c_int32), ("out", _dp), ("stream", _dp), ("transform", C.c_int32), ("_pad", C.c_int32)]
+                ("out_layout", C.c_int32), ("out", _dp), ("stream", _dp), ("transform", C.c_int32), ("stride", C.c_int32),
+                ("age0", C.c_int32), ("out_feats_total", C.c_int32), ("out_feat_offset", C.c_int32), ("_pad", C.c_int32)]
 
 
 class MdgDerived(C.Structure):

@@ -141,6 +141,8 @@ struct WindowArgs {
   int64_t N;
   int F, k, head, n_valid, norm, out_dtype, layout, flat_prefix;
   int xform, Feff, Fout;  // Feff: features the normaliser sees; Fout: features written
+  int stride, age0;       // window row s = ring row of age age0 + (n_valid-1-s)*stride (MultiStackerDiscrete dilations)
+  int Ftot, foff;         // out has Ftot features per row; this window fills columns [foff, foff + Fout)
   int envs;     // envs per block (blockDim.x)
   int sstride;  // smem stride between rows s (doubles)
   int estride;  // smem stride between envs   (doubles)
@@ -155,9 +157,6 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
   const int nv = a.n_valid, F = a.F, k = a.k;
   const bool live = e < a.N;
   double* col = tile + (int64_t)el * a.estride + f;
-  int slot0 = (a.head - (nv - 1)) % k;
-  if (slot0 < 0) slot0 += k;
-
   // phase 1: coalesced ring reads (consecutive envs), column into smem.  Rows older than the env's last
   // reset are not in the ring: they come from the env-major prefix buffer (prices) or are flat (portfolio).
   if (live) {
@@ -167,7 +166,8 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
     // 1.1 ms per 65,536 x 64 x 16 window, profiles/r1_notes.md)
     constexpr int U = 16;
     const int Z = blockDim.z, z = threadIdx.z;  // the column's rows are dealt round-robin to Z threads
-    const int isince = since > nv ? nv : (int)since;             // rows with age < isince come from the ring
+    const int max_age = a.age0 + (nv - 1) * a.stride;
+    const int isince = since > max_age + 1 ? max_age + 1 : (int)since;  // rows with age < isince come from the ring
     const double* rbase = a.ring + (int64_t)f * a.N + e;         // + slot * rstride
     const int64_t rstride = (int64_t)F * a.N;
     // prefix row of age `age`: k - 1 - (age - (since - 1)) = (k - 2 + since) - age
@@ -180,9 +180,9 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
         const int s = z + Z * (j0 + u);
         v[u] = 0.;
         if (s < nv) {
-          const int age = nv - 1 - s;
-          int slot = slot0 + s;
-          if (slot >= k) slot -= k;
+          const int age = a.age0 + (nv - 1 - s) * a.stride;
+          int slot = (a.head - age) % k;
+          if (slot < 0) slot += k;
           if (age < isince) v[u] = rbase[slot * rstride];
           else if (pbase) v[u] = *(pbase - (int64_t)age * F);
           else v[u] = flat;
@@ -297,7 +297,19 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
   const int per_env = nv * Fo;
   const int rows = (int)((a.N - e0) < a.envs ? (a.N - e0) : a.envs);
   const bool f32 = a.out_dtype == MDG_DTYPE_F32, diff = a.xform == MDG_XFORM_RETURNS;
-  if (a.layout == MDG_LAYOUT_NKF && nthr % Fo == 0) {
+  if (a.Ftot != Fo) {  // this window is a column block of a wider output (concatenation over dilations)
+    const int Ft = a.Ftot;
+    for (int re = 0; re < rows; ++re) {
+      for (int r = tid; r < per_env; r += nthr) {
+        const int sr = r / Fo, ff = r - sr * Fo;
+        const double* q = tile + (int64_t)re * a.estride + (int64_t)sr * a.sstride + ff;
+        const double v = diff ? q[1] - q[0] : q[0];
+        const int64_t o = (a.layout == MDG_LAYOUT_NKF) ? ((e0 + re) * nv + sr) * Ft + a.foff + ff
+                                                        : ((e0 + re) * Ft + a.foff + ff) * nv + sr;
+        if (f32) ((float*)a.out)[o] = (float)v; else ((double*)a.out)[o] = v;
+      }
+    }
+  } else if (a.layout == MDG_LAYOUT_NKF && nthr % Fo == 0) {
     // thread -> fixed feature, rows advance by nthr / Fo: consecutive threads write consecutive elements and no
     // index needs a division (a 64-bit div/mod per element made this phase instruction-bound)
     const int ff = tid % Fo, sstep = nthr / Fo;
@@ -562,6 +574,7 @@ static int launch_window_tma(const MdgWindow* w, WindowArgs a) {
   if (!enabled) return 0;
   const int F = a.F, nv = a.n_valid;
   if (a.xform != MDG_XFORM_NONE || a.layout != MDG_LAYOUT_NKF || a.norm == MDG_NORM_EXPANDING) return 0;
+  if (a.stride != 1 || a.age0 != 0 || a.Ftot != a.Fout) return 0;
   int E = env_E, FT = env_FT;
   if (E != 8 && E != 16 && E != 32) return 0;
   if (FT > F) FT = F;
@@ -747,6 +760,13 @@ extern "C" int mdg_materialise_window(const MdgWindow* w) {
   a.ring = w->ring; a.prefix = w->prefix; a.timestamp = w->timestamp; a.reset_ts = w->reset_ts;
   a.out = w->out; a.N = w->n_envs; a.F = n_feats; a.k = window; a.head = head; a.n_valid = n_valid;
   a.norm = w->norm_type; a.out_dtype = w->out_dtype; a.layout = w->out_layout; a.flat_prefix = w->flat_prefix;
+  a.stride = w->stride > 1 ? w->stride : 1;
+  a.age0 = w->age0 > 0 ? w->age0 : 0;
+  if (a.age0 + (int64_t)(n_valid - 1) * a.stride >= window)
+    return set_err(MDG_E_INVALID, "dilated window reaches beyond the ring (need window >= age0 + (n_valid-1)*stride + 1)");
+  a.Ftot = w->out_feats_total > 0 ? w->out_feats_total : a.Fout;
+  a.foff = w->out_feats_total > 0 ? w->out_feat_offset : 0;
+  if (a.foff < 0 || a.foff + a.Fout > a.Ftot) return set_err(MDG_E_INVALID, "bad out_feat_offset / out_feats_total");
   {
     const int t = launch_window_tma(w, a);
     if (t != 0) return t < 0 ? t : MDG_OK;

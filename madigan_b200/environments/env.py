@@ -625,11 +625,13 @@ class Env:
 
     # ------------------------------------------------------------------ window / stats / checkpoint
     def window(self, norm_type=None, dtype=torch.float64, channels_first=False, n_valid=None, out=None,
-               transform=A.XFORM_NONE):
+               transform=A.XFORM_NONE, stride=1, age0=0, out_feat_offset=None):
         """Materialise the price window ``(N, n_valid, nF)`` (or ``(N, nF, n_valid)``) from the observation
         ring, normalised as ``make_normalizer(norm_type)`` (reference: utils/preprocessor.py:53-107,183-189).
         ``transform``: ``XFORM_PAIR_RATIO`` (StackerDiscretePairs, nF 2 -> 1) or ``XFORM_RETURNS``
-        (StackerDiscreteReturns, nF -> nF-1)."""
+        (StackerDiscreteReturns, nF -> nF-1).  ``stride`` / ``age0``: a dilated window -- row s is the ring row of age
+        ``age0 + (n_valid-1-s)*stride`` (MultiStackerDiscrete); with ``out_feat_offset`` the window is written into
+        the column block ``[offset, offset + nF)`` of a wider ``out`` (the concatenation over dilations)."""
         from ..utils.preprocessor import NORM_TYPES
         nv = self.n_valid if n_valid is None else int(n_valid)
         norm = NORM_TYPES[norm_type]
@@ -638,35 +640,46 @@ class Env:
         if out is None:
             out = torch.empty(shape, dtype=dtype, device=self.device)
         dt = A.DTYPE_F32 if out.dtype == torch.float32 else A.DTYPE_F64
+        ftot = 0
+        if out_feat_offset is not None:
+            ftot = out.shape[1] if channels_first else out.shape[2]
         self._window_launch(self.t["obs_price"], self.t["pre_price"], 0, self.nA, nv, norm, out, dt,
-                            A.LAYOUT_NFK if channels_first else A.LAYOUT_NKF, transform)
+                            A.LAYOUT_NFK if channels_first else A.LAYOUT_NKF, transform, stride, age0, ftot,
+                            out_feat_offset or 0)
         return out
 
-    def _window_launch(self, ring, prefix, flat_prefix, n_feats, nv, norm, out, dt, layout, transform=A.XFORM_NONE):
+    def _window_launch(self, ring, prefix, flat_prefix, n_feats, nv, norm, out, dt, layout, transform=A.XFORM_NONE,
+                       stride=1, age0=0, ftot=0, foff=0):
         w = A.MdgWindow(ring=ring.data_ptr(), prefix=None if prefix is None else prefix.data_ptr(),
                         timestamp=self.t["timestamp"].data_ptr(), reset_ts=self.t["reset_ts"].data_ptr(),
                         n_envs=self.N, n_feats=n_feats, window=self.k, head=self.head, n_valid=nv, norm_type=norm,
                         flat_prefix=flat_prefix, out_dtype=dt, out_layout=layout, out=out.data_ptr(),
-                        stream=self._sptr(), transform=transform)
+                        stream=self._sptr(), transform=transform, stride=int(stride), age0=int(age0),
+                        out_feats_total=int(ftot), out_feat_offset=int(foff))
         with torch.cuda.device(self.device):
             check(self._lib.mdg_materialise_window(C.byref(w)))
         self.launches += 1
 
-    def portfolio_window(self, n_valid=None):
+    def portfolio_window(self, n_valid=None, stride=1, age0=0):
         """(N, n_valid, nA+1) window of ledgerNormedFull rows, oldest first (rows older than the env's last
         reset are the flat portfolio [1,0,...,0] of its history fill)."""
         nv = self.n_valid if n_valid is None else int(n_valid)
         out = torch.empty((self.N, nv, self.nA + 1), dtype=torch.float64, device=self.device)
-        self._window_launch(self.t["obs_port"], None, 1, self.nA + 1, nv, A.NORM_NONE, out, A.DTYPE_F64, A.LAYOUT_NKF)
+        self._window_launch(self.t["obs_port"], None, 1, self.nA + 1, nv, A.NORM_NONE, out, A.DTYPE_F64, A.LAYOUT_NKF,
+                            A.XFORM_NONE, stride, age0)
         return out
 
-    def time_window(self, n_valid=None):
+    def time_window(self, n_valid=None, stride=1, age0=0):
         nv = self.n_valid if n_valid is None else int(n_valid)
         out = torch.empty((self.N, nv), dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
             check(self._lib.mdg_materialise_time(self.t["timestamp"].data_ptr(), self.N, nv, out.data_ptr(),
                                                  self._sptr()))
         self.launches += 1
+        if stride != 1 or age0 != 0:  # timestamp[e] - (age0 + (nv-1-s)*stride): every ring row is one generator tick
+            with self._copy_ctx():
+                ages = age0 + (nv - 1 - torch.arange(nv, device=self.device)) * stride
+                out = self.t["timestamp"][:, None] - ages[None, :]
         return out
 
     def episode_stats(self):

@@ -36,6 +36,8 @@ def make_preprocessor(config, n_feats):
         return StackerDiscretePairs.from_config(config, n_feats)
     if ptype == "StackerDiscreteReturns":
         return StackerDiscreteReturns.from_config(config, n_feats)
+    if ptype == "MultiStackerDiscrete":
+        return MultiStackerDiscrete.from_config(config, n_feats)
     raise NotImplementedError(f"{ptype} is not implemented ")
 
 
@@ -141,3 +143,97 @@ class StackerDiscreteReturns(StackerDiscrete):
     """reference: utils/preprocessor.py:324-333 -- normaliser, then ``np.diff(price)``, which runs over the LAST
     axis (features): price (k, nF-1); portfolio and timestamp lose their first row."""
     transform = A.XFORM_RETURNS
+
+
+class MultiStackerDiscrete:
+    """reference: utils/preprocessor.py:202-288 -- one window of ``window_len`` rows per dilation d, holding every d-th
+    streamed state (the first streamed state, then every d-th after it); ``current_data().price`` is their
+    concatenation over the feature axis, (N, k, n_feats * len(dilations)), normalised; portfolio and timestamp come
+    from the first dilation.
+
+    No deques here either: the env-owned observation ring already holds every row, so a dilated window is the ring
+    read with a stride (one window-kernel launch per dilation, each writing its column block of the output).  The
+    env's ring must be deep enough: ``Env(window=...) >= window_len * max(dilations)``.  Column-wise normalisers only
+    (``expanding`` runs across the concatenated features in the reference; not supported with several dilations)."""
+
+    def __init__(self, window_len, dilations, n_feats, norm=True, norm_type="standard_normal", dtype=torch.float64):
+        self.k = int(window_len)
+        self.dilations = [int(d) for d in dilations]
+        if not self.dilations or min(self.dilations) < 1:
+            raise ValueError("dilations must be positive")
+        self.min_tf = self.k
+        self.norm = bool(norm)
+        self.norm_type = norm_type if self.norm else None
+        if self.norm:
+            make_normalizer(norm_type)
+            if norm_type == "expanding" and len(self.dilations) > 1:
+                raise NotImplementedError("'expanding' runs across the concatenated features; not supported here")
+        self.max_dilation = max(self.dilations)
+        self.n_feats = int(n_feats)
+        self.dtype = dtype
+        self._feature_output_shape = (self.k, self.n_feats * len(self.dilations))
+        self._env = None
+        self._count = 0  # states streamed since reset_state
+
+    @property
+    def feature_output_shape(self):
+        return self._feature_output_shape
+
+    @classmethod
+    def from_config(cls, config, n_feats):
+        get = (lambda c, k_, d=None: c.get(k_, d)) if isinstance(config, dict) else \
+              (lambda c, k_, d=None: c[k_] if k_ in c.keys() else d)
+        pconf = config["preprocessor_config"] if isinstance(config, dict) else config.preprocessor_config
+        return cls(get(pconf, "window_length"), get(pconf, "dilations"), n_feats, get(pconf, "norm", False),
+                   get(pconf, "norm_type", None))
+
+    def _len_of(self, d):
+        """rows the reference's deque of dilation d holds after `_count` streamed states (:247-258)"""
+        return min(self.k, (self._count + d - 1) // d)
+
+    def __len__(self):
+        return self._len_of(self.max_dilation)
+
+    def _bind(self, env):
+        if self._env is not None and self._env is not env:
+            raise ValueError("a MultiStackerDiscrete serves one Env (the ring is env-owned)")
+        if env.k < self.k * self.max_dilation:
+            raise ValueError(f"the env's observation ring ({env.k} rows) is shorter than window_length * max dilation "
+                             f"= {self.k * self.max_dilation}")
+        self._env = env
+
+    def stream_state(self, state):
+        ring = getattr(state, "_ring", None)
+        if ring is None:
+            raise TypeError("MultiStackerDiscrete consumes States produced by madigan_b200 Env.step/reset")
+        self._bind(ring[0])
+        self._count += 1
+
+    def stream(self, data):
+        self.stream_state(data[0] if isinstance(data, tuple) else data)
+
+    def current_data(self):
+        env = self._env
+        if env is None or self._count == 0:
+            raise RuntimeError("no data streamed yet")
+        lens = [self._len_of(d) for d in self.dilations]
+        if len(set(lens)) != 1:  # np.concatenate of unequal deques raises in the reference too
+            raise ValueError("the dilated windows have different lengths; call initialize_history first")
+        nv, D, nF = lens[0], len(self.dilations), self.n_feats
+        price = torch.empty((env.N, nv, nF * D), dtype=self.dtype, device=env.device)
+        for i, d in enumerate(self.dilations):
+            age0 = (self._count - 1) % d  # the newest state the deque of dilation d holds
+            env.window(self.norm_type, n_valid=nv, out=price, stride=d, age0=age0, out_feat_offset=i * nF)
+        d0 = self.dilations[0]
+        a0 = (self._count - 1) % d0
+        return State(price, env.portfolio_window(nv, stride=d0, age0=a0), env.time_window(nv, stride=d0, age0=a0))
+
+    def initialize_history(self, env):
+        """reference :281-284 -- no-action steps until the longest-dilation window is full."""
+        self._bind(env)
+        while len(self) < self.k:
+            _state, _reward, _done, _info = env.step()
+            self.stream_state(_state)
+
+    def reset_state(self):
+        self._count = 0
