@@ -45,3 +45,59 @@ def get_env_info(env):
         "ledger": env.ledger.clone(),
         "ledgerNormed": env.ledgerNormed.clone(),
     }
+
+
+class SingleEnv:
+    """A one-env view of a batched ``Env(n_envs=1)`` that speaks the reference's single-env dialect: numpy arrays
+    without the leading batch axis and Python scalars, so that the reference's agent loop (``offpolicy_q.py:136-205``:
+    ``prev_eq = env.equity``, ``env.step(transaction)``, ``info.brokerResponse.transactionUnits`` ...) runs on it
+    unmodified.  Every read is a device-to-host copy: this is the compatibility path, not the fast one -- the batched
+    ``Env`` with in-kernel rewards and ``DeviceReplay`` is."""
+    _ARRAYS = ("currentPrices", "currentData", "ledger", "meanEntryPrices", "borrowedMarginLedger", "positionValues",
+               "positionValuesFull", "pnlPositions", "ledgerFull", "ledgerNormed", "ledgerNormedFull",
+               "ledgerAbsNormed", "ledgerAbsNormedFull")
+    _SCALARS = ("cash", "equity", "assetValue", "pnl", "balance", "availableMargin", "usedMargin", "borrowedMargin",
+                "borrowedAssetValue")
+
+    def __init__(self, env):
+        if env.N != 1:
+            raise ValueError("SingleEnv wraps an Env built with n_envs=1")
+        self._env = env
+
+    def __getattr__(self, name):
+        env = self.__dict__["_env"]
+        if name in SingleEnv._ARRAYS:
+            return getattr(env, name)[0].cpu().numpy()
+        if name in SingleEnv._SCALARS:
+            return float(getattr(env, name)[0])
+        if name in ("timestamp", "currentTime"):
+            return int(env.timestamp[0])
+        return getattr(env, name)
+
+    @staticmethod
+    def _state(st):
+        from ..utils.data import State
+        return State(st.price[0].cpu().numpy(), st.portfolio[0].cpu().numpy(), int(st.timestamp[0]), _ring=st._ring)
+
+    def _out(self, out):
+        from ..utils.data import BrokerResponse, EnvInfo
+        st, reward, done, info = out
+        br = info.brokerResponse
+        resp = BrokerResponse(br.event, int(br.timestamp[0]), br.transactionPrice[0].cpu().numpy(),
+                              br.transactionUnits[0].cpu().numpy(), br.transactionCost[0].cpu().numpy(),
+                              br.riskInfo[0].cpu().numpy(), bool(br.marginCall[0]))
+        return self._state(st), float(reward[0]), bool(done[0]), EnvInfo(resp, info.dataEnd)
+
+    def step(self, *args):
+        import numpy as np
+        import torch
+        conv = [a if isinstance(a, (str, int)) and i == 0 and len(args) == 2
+                else torch.as_tensor(np.asarray(a, dtype=np.float64)).reshape(1, -1) if len(args) == 1
+                else torch.as_tensor(np.asarray(a, dtype=np.float64)).reshape(1) for i, a in enumerate(args)]
+        return self._out(self._env.step(*conv))
+
+    def reset(self):
+        return self._state(self._env.reset())
+
+    def checkRisk(self):
+        return int(self._env.checkRisk()[0])
