@@ -328,70 +328,81 @@ def run_ours(args):
     join()
     barrier()
 
-    # ---- timed region 1: device-resident inputs ("value").  The K steps are issued R times (`--repeats`); the line
-    # reports the MEDIAN repeat.  With `--graph` (default for K <= 512) the K-step sequence of a repeat -- 2 launches
-    # per step, forked over the streams -- is captured into one CUDA graph beforehand and the timed region is its
-    # launch: a 20-step region is ~1 ms of device work, less than the host needs to enqueue 40 launches one by one.
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
+    # ---- timed regions.  The K steps of a region are issued R times (`--repeats`); the line reports the MEDIAN
+    # repeat.  With `--graph` (default for K <= 512) the K-step sequence of a repeat -- kernels and, for the
+    # end-to-end regions, the pinned-host copies, forked over the streams -- is captured into one CUDA graph
+    # beforehand and the timed region is its launch: a 20-step region is ~1 ms of device work, less than the host
+    # needs to enqueue it call by call.  The calls that are captured are the public ones (Env.step ...).
     R_ = max(1, args.repeats)
     use_graph = args.graph == "on" or (args.graph == "auto" and K <= 512)
     cap = torch.cuda.Stream(dev)  # capture origin stream
-    graphs = []
-    step_no = W
-    t_issue = None
-    if use_graph:
-        for r_ in range(R_):
-            g_ = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize(dev)
-            with torch.cuda.stream(cap):
-                g_.capture_begin(capture_error_mode="thread_local")
-                ev_f = torch.cuda.Event()
-                ev_f.record(cap)
-                for st in streams:
-                    st.wait_event(ev_f)
-                for i in range(K):
-                    step_slab(step_no + i, acts[i % len(acts)])
-                for st in streams:
-                    e_ = torch.cuda.Event()
-                    e_.record(st)
-                    cap.wait_event(e_)
-                g_.capture_end()
-            step_no += K
-            graphs.append(g_)
-    launches0 = sum(e.launches for e in envs)
-    ms_all = []
-    barrier()
-    t_region0 = time.perf_counter()
-    for r_ in range(R_):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+    counters = {"step_no": W, "t_issue": None}
+
+    def timed_region(step_fn, restore_stream=False):
+        """-> list of R_ region times (ms), each K calls of step_fn(i)"""
+        graphs = []
         if use_graph:
-            with torch.cuda.stream(cap):
-                ev0.record(cap)
-                graphs[r_].replay()
-                ev1.record(cap)
-        else:
-            ev0.record(stream)
-            fork(ev0)
-            t_i = time.perf_counter()
-            for i in range(K):
-                step_slab(step_no + i, acts[i % len(acts)])
-            t_i = (time.perf_counter() - t_i) / K * 1e3  # host time to enqueue one step (must stay below ms_per_step)
-            t_issue = t_i if t_issue is None else min(t_issue, t_i)
-            step_no += K
-            join()
-            ev1.record(stream)
+            for r_ in range(R_):
+                g_ = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(dev)
+                with torch.cuda.stream(cap):
+                    g_.capture_begin(capture_error_mode="thread_local")
+                    ev_f = torch.cuda.Event()
+                    ev_f.record(cap)
+                    for st in streams:
+                        st.wait_event(ev_f)
+                    for i in range(K):
+                        step_fn(counters["step_no"] + i)
+                    if restore_stream:
+                        torch.cuda.set_stream(cap)
+                    for st in streams:
+                        e_ = torch.cuda.Event()
+                        e_.record(st)
+                        cap.wait_event(e_)
+                    g_.capture_end()
+                counters["step_no"] += K
+                graphs.append(g_)
+        out = []
         barrier()
-        ms_all.append(ev0.elapsed_time(ev1))
-    launches = (2 * K * R_) if use_graph else (sum(e.launches for e in envs) - launches0)
-    launches //= R_
+        for r_ in range(R_):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            if use_graph:
+                with torch.cuda.stream(cap):
+                    ev0.record(cap)
+                    graphs[r_].replay()
+                    ev1.record(cap)
+            else:
+                ev0.record(stream)
+                fork(ev0)
+                t_i = time.perf_counter()
+                for i in range(K):
+                    step_fn(counters["step_no"] + i)
+                t_i = (time.perf_counter() - t_i) / K * 1e3  # host time to enqueue one step
+                counters["t_issue"] = t_i if counters["t_issue"] is None else min(counters["t_issue"], t_i)
+                counters["step_no"] += K
+                if restore_stream:
+                    torch.cuda.set_stream(stream)
+                join()
+                ev1.record(stream)
+            barrier()
+            out.append(ev0.elapsed_time(ev1))
+        return out
+
+    # ---- timed region 1: device-resident inputs ("value")
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = sum(e.launches for e in envs)
+    t_region0 = time.perf_counter()
+    ms_all = timed_region(lambda i: step_slab(i, acts[i % len(acts)]))
+    launches = (sum(e.launches for e in envs) - launches0) // R_
     ms_total = sorted(ms_all)[len(ms_all) // 2]
     t_region1 = time.perf_counter()
     sampler.stop()
     clocks = sampler.summary(t_region0, t_region1)
-    del graphs
+    step_no = counters["step_no"]
+    t_issue = counters["t_issue"]
 
     # ---- the dominant kernel alone (roofline): the step kernel of consecutive slabs back to back on ONE stream,
     # CUDA events around every launch, resets outside the event pairs
@@ -433,16 +444,8 @@ def run_ours(args):
     set_stream(stream)
     join()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    fork(e0)
-    for i in range(K):
-        e2e_step(i)
-    set_stream(stream)
-    join()
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_all = timed_region(e2e_step, restore_stream=True)
+    e2e_ms = sorted(e2e_all)[len(e2e_all) // 2]
 
     # ---- timed region 3 (extra key "e2e_actions"): the same end-to-end loop through Env.step_actions -- the agent's
     # DISCRETE actions (1 byte per asset) cross PCIe and DQN.action_to_transaction (dqn.py:160-179) runs fused in
@@ -466,16 +469,8 @@ def run_ours(args):
     set_stream(stream)
     join()
     barrier()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record(stream)
-    fork(a0)
-    for i in range(K):
-        e2e_actions_step(i)
-    set_stream(stream)
-    join()
-    a1.record(stream)
-    barrier()
-    e2e_act_ms = a0.elapsed_time(a1)
+    e2e_act_all = timed_region(e2e_actions_step, restore_stream=True)
+    e2e_act_ms = sorted(e2e_act_all)[len(e2e_act_all) // 2]
     for e_ in envs:
         e_.bind_stream(None)
     h2d = ENVS_PER_GPU * N_ASSETS * 8
@@ -513,7 +508,7 @@ def run_ours(args):
                             "h2d_bytes_per_step": ENVS_PER_GPU * N_ASSETS, "d2h_bytes_per_step": d2h,
                             "api": "Env.step_actions(int8 actions, action_atoms=3, unit_size=.05): "
                                    "DQN.action_to_transaction fused in front of the step"},
-            "gpu_launches": launches, "repeats": R_, "ms_per_repeat": ms_all,
+            "gpu_launches": launches, "repeats": R_, "ms_per_repeat": ms_all, "e2e_ms_per_repeat": e2e_all,
             "timed_region": ("one CUDA graph launch per repeat (K steps x 2 kernels, forked over the streams)"
                              if use_graph else "K eager Env.step(auto_reset=True) calls"),
             "host_issue_ms_per_step": t_issue, "host_cores_bound": numa_cores, "clocks": clocks,
