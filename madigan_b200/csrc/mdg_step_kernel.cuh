@@ -24,6 +24,10 @@ struct StepArgs {
   MdgStepIO IO;
   MdgLaunch L;
   int units_v2;     // set by launch_step: the units matrix can be read with 16-byte loads (aligned base, even nA)
+  // constants of the risk gates, filled by launch_step: as kernel parameters they are constant-bank operands of the
+  // instructions that use them instead of ten live registers per thread (the one-wave variant spills at 128)
+  double c_reqM, c_maintM, c_band_scale, c_g1, c_g2;
+  int c_reqM_ok, c_force_exact;
   int* done_count;  // nullable (auto-reset): number of envs that finished this step ...
   int* done_list;   // ... and their indices, appended warp by warp in the kernel's tail
 };
@@ -275,12 +279,7 @@ struct StepAcc {
   bool bad_risk;
 };
 
-struct StepConsts {
-  double reqM, maintM, band_scale;
-  double g1, g2;  // magnitude-bound coefficients of one transaction (tx_asset)
-  bool reqM_ok;
-  bool force_exact;  // MdgLaunch.flags & MDG_FLAG_FORCE_EXACT_GATE: every gate takes the exact (cold) path
-};
+struct StepConsts {};  // the gate constants are kernel parameters (StepArgs.c_*); `c` is passed along as a tag
 
 // Broker::handleTransaction(port, i, units) (Broker.cpp:124-142) for one asset whose state is in registers:
 // risk gate (Portfolio.cpp:254-279), slippage/cost (Broker.cpp:171-178), ledger update (Portfolio.cpp:284-323).
@@ -291,6 +290,7 @@ struct StepConsts {
 // (G = sum of magnitudes); a decision is taken from the running sums only when it clears its threshold by
 // 1e-9 * G.  Otherwise -- a knife-edge, NaN/Inf, a non-positive required margin -- the exact left-to-right
 // folds decide (exact_gate).  Decisions, and therefore ledgers, are bit-identical to the oracle's either way.
+template <bool TX2>
 __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c, StepAcc& A, int64_t N, int64_t e,
                                          int na, int i, double price, double& cur, double& mep, double& bm,
                                          double units, double& tp, double& tu, double& tc, int& risk,
@@ -305,19 +305,34 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
     if (!opposite || units > -1 * cur) {  // Portfolio.cpp:257-258: only these orders are gated
       const double amt = fabs(price * (opposite ? units + cur : units));
       const double bal = A.cash + A.rSE, pnl = A.rAV - A.rML, x = bal + pnl;
-      const double band = c.band_scale * (A.G + amt);
-      const double d1 = x - amt * c.reqM;  // availableMargin <= |amount|  <=>  d1 <= 0
-      bool certain = c.reqM_ok && fabs(d1) > band && fabs(bal) > band;
-      int r_fast = (d1 <= 0. || bal <= 0.) ? MDG_RISK_INSUFF_MARGIN : MDG_RISK_GREEN;
-      if (!opposite) {  // Portfolio::checkRisk() first (:268), :243-252
-        const double m = c.maintM * pnl;
-        const double d3 = (A.cash + A.rAV - A.rBM) + m, d4 = x + m;
-        certain = certain && fabs(d3) > band && fabs(d4) > band;
-        if (d3 <= 0. || d4 <= 0.) r_fast = MDG_RISK_MARGIN_CALL;
+      const double band = a.c_band_scale * (A.G + amt);
+      const double d1 = x - amt * a.c_reqM;  // availableMargin <= |amount|  <=>  d1 <= 0
+      bool certain;
+      int r_fast;
+      if constexpr (TX2) {
+        // multi-wave variant (168 registers): predicate arithmetic instead of short-circuit branches, the same
+        // decisions; 3.5 % faster at 1 M envs, but it costs registers the one-wave variant does not have
+        const double m = a.c_maintM * pnl;
+        const double d3 = (A.cash + A.rAV - A.rBM) + m, d4 = x + m;  // Portfolio::checkRisk() first (:268), :243-252
+        const bool ok1 = (fabs(d1) > band) & (fabs(bal) > band);
+        const bool ok2 = (fabs(d3) > band) & (fabs(d4) > band);
+        certain = a.c_reqM_ok & ok1 & (opposite | ok2);
+        const bool insuff = (d1 <= 0.) | (bal <= 0.);
+        const bool mcall = !opposite & ((d3 <= 0.) | (d4 <= 0.));
+        r_fast = mcall ? MDG_RISK_MARGIN_CALL : (insuff ? MDG_RISK_INSUFF_MARGIN : MDG_RISK_GREEN);
+      } else {
+        certain = a.c_reqM_ok && fabs(d1) > band && fabs(bal) > band;
+        r_fast = (d1 <= 0. || bal <= 0.) ? MDG_RISK_INSUFF_MARGIN : MDG_RISK_GREEN;
+        if (!opposite) {  // Portfolio::checkRisk() first (:268), :243-252
+          const double m = a.c_maintM * pnl;
+          const double d3 = (A.cash + A.rAV - A.rBM) + m, d4 = x + m;
+          certain = certain && fabs(d3) > band && fabs(d4) > band;
+          if (d3 <= 0. || d4 <= 0.) r_fast = MDG_RISK_MARGIN_CALL;
+        }
       }
-      risk = (certain && !c.force_exact)
+      risk = (certain && !a.c_force_exact)
                  ? r_fast
-                 : exact_gate(S, N, e, na, A.cash, c.reqM, c.maintM, i, units, A.pav, A.pml, A.pbm, A.pse);
+                 : exact_gate(S, N, e, na, A.cash, a.c_reqM, a.c_maintM, i, units, A.pav, A.pml, A.pbm, A.pse);
     }
     if (risk == MDG_RISK_GREEN) {
       // Broker::applySlippage / getTransactionCost  Broker.cpp:171-178
@@ -339,16 +354,27 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
         mep += (transactionPrice - mep) * (units / (units + cur));
       }
       const double amount = transactionPrice * units;
-      const double marginToUse = amount * c.reqM;
+      const double marginToUse = amount * a.c_reqM;
       const double marginToBorrow = amount - marginToUse;
       bm += marginToBorrow;
       A.cash -= (marginToUse + transactionCost);
       cur += units;
-      if (fabs(cur) < 0.000001) {
-        mep = 0.;
-        if (bm > 0.) { A.cash -= bm; bm = 0.; }
+      if constexpr (TX2) {
+        const bool flat = fabs(cur) < 0.000001;
+        mep = flat ? 0. : mep;
+        const bool ra_ = flat & (bm > 0.);
+        A.cash = ra_ ? A.cash - bm : A.cash;
+        bm = ra_ ? 0. : bm;
+        const bool rb_ = bm < 0.;
+        A.cash = rb_ ? A.cash - bm : A.cash;
+        bm = rb_ ? 0. : bm;
+      } else {
+        if (fabs(cur) < 0.000001) {
+          mep = 0.;
+          if (bm > 0.) { A.cash -= bm; bm = 0.; }
+        }
+        if (bm < 0.) { A.cash -= bm; bm = 0.; }
       }
-      if (bm < 0.) { A.cash -= bm; bm = 0.; }
       gst(&S.ledger[(int64_t)i * N + e], cur);
       gst(&S.mean_entry[(int64_t)i * N + e], mep);
       gst(&S.borrowed[(int64_t)i * N + e], bm);
@@ -361,7 +387,7 @@ __device__ __forceinline__ void tx_asset(const StepArgs& a, const StepConsts& c,
       // every new term's magnitude is at most its old magnitude (already in G) plus |units|*(|price|+|tp|), three
       // terms, plus the cost; with |tp| <= |price|(1+|slip_rel|)+|slip_abs| and |cost| <= |units price||tc_rel|+|tc_abs|
       // that is |units| * (|price| * g1 + g2) (+ |tc_abs|, added once per asset in the prologue)
-      A.G += fabs(tu) * (fabs(price) * c.g1 + c.g2);
+      A.G += fabs(tu) * (fabs(price) * a.c_g1 + a.c_g2);
     } else if (risk != MDG_RISK_INSUFF_MARGIN) {
       A.bad_risk = true;
     }
@@ -461,7 +487,7 @@ __device__ __forceinline__ int gen_state_rows(const MdgAssetGen& g) {
 //     wave (that launch is latency-bound: a second wave would cost as much as the first);
 //   168 registers -> 3 blocks per SM, no spills: best throughput when there are many waves (>= 262,144 envs).
 // (64-thread blocks x 7 per SM at 144 registers were measured slower than either.)
-template <bool PAIRS, int BS, bool ACTIONS>
+template <bool PAIRS, int BS, bool ACTIONS, bool TX2>
 __device__ __forceinline__ void step_body(const StepArgs& a) {
   // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff (and, in the
   // all-pairs kernel, this step's normals before they are consumed; see stash_normal_row)
@@ -546,14 +572,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
     for (int j = 1; j <= na; ++j) w_sum = w_sum + wrow[j];
   }
 
-  StepConsts c;
-  c.reqM = P.required_margin;
-  c.maintM = P.maintenance_margin;
-  c.reqM_ok = c.reqM > 0. && c.reqM <= 1e6;
-  c.band_scale = 1e-9 * (1. + fabs(c.maintM)) * (c.reqM > 1. ? c.reqM : 1.);
-  c.g1 = 6. + 3. * fabs(P.slippage_rel) + fabs(P.tcost_rel);
-  c.g2 = 3. * fabs(P.slippage_abs);
-  c.force_exact = (a.L.flags & MDG_FLAG_FORCE_EXACT_GATE) != 0;
+  const StepConsts c{};  // (tag: the values live in the kernel parameters, StepArgs.c_*)
   A.G += na * fabs(P.tcost_abs);  // the absolute cost of up to nA transactions
 
   const uint32_t gid = (uint32_t)(a.L.env_offset + e);
@@ -608,7 +627,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       for (int q = 0; q < 2; ++q) {
         const int i = 2 * p + q;
         if (mode == MDG_MODE_SINGLE) units[q] = (i == a.L.asset_idx) ? urow[0] : 0.;
-        tx_asset(a, c, A, N, e, na, i, price[q], cur[q], mep[q], bm[q], units[q], tp[q], tu[q], tc[q], risk[q],
+        tx_asset<TX2>(a, c, A, N, e, na, i, price[q], cur[q], mep[q], bm[q], units[q], tp[q], tu[q], tc[q], risk[q],
                  prev_val[q]);
       }
       // OUPair::getData, DataSource.cpp:1232-1240 (draw order rw, x0, x1)
@@ -652,7 +671,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       else if (mode == MDG_MODE_SINGLE && i == a.L.asset_idx) units = urow[0];
       double tp, tu, tc, prev_val;
       int risk;
-      tx_asset(a, c, A, N, e, na, i, price, cur, mep, bm, units, tp, tu, tc, risk, prev_val);
+      tx_asset<TX2>(a, c, A, N, e, na, i, price, cur, mep, bm, units, tp, tu, tc, risk, prev_val);
       // generator tick of this asset (DataSource.cpp getData family)
       const MdgAssetGen& g = P.gen[i];
       double newp;
@@ -675,7 +694,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
     }
   }
 
-  const double cash = A.cash, nav = A.nav, pml = A.pml, pbm = A.pbm, pse = A.pse, maintM = c.maintM;
+  const double cash = A.cash, nav = A.nav, pml = A.pml, pbm = A.pbm, pse = A.pse, maintM = a.c_maintM;
   const int head = a.L.head;
   // BrokerResponse.marginCall (Broker.cpp:135,156): Portfolio::checkRisk() after the last transaction
   if (mode != MDG_MODE_HOLD) a.IO.margin_call[e] = margin_call(cash, A.pav, pml, pbm, pse, maintM) ? 1 : 0;
@@ -807,7 +826,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
 
 template <bool PAIRS, int BS, int MINB, bool ACTIONS>
 __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ StepArgs a) {
-  step_body<PAIRS, BS, ACTIONS>(a);
+  step_body<PAIRS, BS, ACTIONS, (MINB < 4)>(a);  // MINB 3 = the multi-wave register budget
 }
 
 // host side: is every asset part of an OUPair laid out (role0, role1) with in-order noise slots?
@@ -835,6 +854,13 @@ static inline int launch_step(StepArgs& a) {
   const int64_t N = a.L.n_envs;
   cudaStream_t st = (cudaStream_t)a.L.stream;
   const bool pairs = all_ou_pairs(a.P);
+  a.c_reqM = a.P.required_margin;
+  a.c_maintM = a.P.maintenance_margin;
+  a.c_reqM_ok = (a.c_reqM > 0. && a.c_reqM <= 1e6) ? 1 : 0;
+  a.c_band_scale = 1e-9 * (1. + fabs(a.c_maintM)) * (a.c_reqM > 1. ? a.c_reqM : 1.);
+  a.c_g1 = 6. + 3. * fabs(a.P.slippage_rel) + fabs(a.P.tcost_rel);
+  a.c_g2 = 3. * fabs(a.P.slippage_abs);
+  a.c_force_exact = (a.L.flags & MDG_FLAG_FORCE_EXACT_GATE) ? 1 : 0;
   const unsigned grid = (unsigned)((N + 127) / 128);
   a.units_v2 = (a.IO.units && (reinterpret_cast<uintptr_t>(a.IO.units) & 15) == 0 && a.P.n_assets % 2 == 0) ? 1 : 0;
   const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128;

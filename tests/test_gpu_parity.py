@@ -383,3 +383,32 @@ def test_step_autoreset_single_call_equals_two_calls():
             a = envs[0].t[name]
             assert torch.equal(a, envs[1].t[name]) and torch.equal(a, envs[2].t[name]), (t, name)
     assert n_done > 20
+
+
+@pytest.mark.gpu
+def test_multi_wave_kernel_variant_parity():
+    """Launches above 151,552 envs take the multi-wave instantiation of the step kernel (168-register budget, predicate
+    arithmetic in the gate): the same oracle comparison as everywhere else, at 155,648 envs x 16 assets with DSR."""
+    N = 155_648
+    reward = dict(reward_shaper_config={"reward_shaper": "DSR", "adaptation_rate": .001}, nstep_return=1, discount=.99,
+                  reduce_rewards=True)
+    env, orc, P = make_pair("pairs8", N, 8, reward, (1., .25), (.02, 0., .001, 0.))
+    rng = np.random.default_rng(1)
+    orc.reset(fill_ticks=1, clear_nstep=False)
+    sync_state_from_oracle(env, orc)
+    nz, uz = noise(rng, P, N, ticks=8)
+    env.reset(fill_history=True, normals=nz, uniforms=uz)
+    orc.reset(fill_ticks=8, normals=nz, uniforms=uz)
+    seen = set()
+    for t in range(8):
+        units = (rng.integers(-1, 2, size=(N, 16)) * 9000.).astype(np.float64)
+        nz, uz = noise(rng, P, N)
+        env.step(torch.from_numpy(units), normals=nz, uniforms=uz)
+        orc.step(units, normals=nz, uniforms=uz)
+        compare_step(env, orc, True, t, shaped=True)
+        seen |= set(np.unique(orc.risk).tolist())
+        if orc.done.any():
+            nz, uz = noise(rng, P, N, ticks=8)
+            env.reset(mask=torch.from_numpy(orc.done.copy()), fill_history=True, normals=nz, uniforms=uz)
+            orc.reset(mask=orc.done.copy(), fill_ticks=8, normals=nz, uniforms=uz)
+    assert len(seen) >= 2
