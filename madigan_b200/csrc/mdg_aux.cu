@@ -181,7 +181,7 @@ __global__ void window_kernel(const __grid_constant__ WindowArgs a) {
         v[u] = 0.;
         if (s < nv) {
           const int age = a.age0 + (nv - 1 - s) * a.stride;
-          int slot = (a.head - age) % k;
+          int slot = a.head - age;  // age <= k - 1 (checked by the launcher): one wrap at most
           if (slot < 0) slot += k;
           if (age < isince) v[u] = rbase[slot * rstride];
           else if (pbase) v[u] = *(pbase - (int64_t)age * F);
