@@ -28,6 +28,7 @@ struct StepArgs {
   // instructions that use them instead of ten live registers per thread (the one-wave variant spills at 128)
   double c_reqM, c_maintM, c_band_scale, c_g1, c_g2;
   int c_reqM_ok, c_force_exact;
+  int bulk;  // set by launch_step: the pairs' state rows reach the block through cp.async.bulk + mbarrier (see step_body)
   int* done_count;  // nullable (auto-reset): number of envs that finished this step ...
   int* done_list;   // ... and their indices, appended warp by warp in the kernel's tail
 };
@@ -54,6 +55,24 @@ constexpr int kBlock = 128;
 #define MDG_AB_L1 0
 #endif
 constexpr int kRngUnroll = MDG_RNG_UNROLL, kTailUnroll = MDG_TAIL_UNROLL;  // #pragma unroll does not expand macros
+
+// ---- bulk-copy staging of the state rows (sm_90+: cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS)
+constexpr int kBulkRows = 9;    // per pair: price x2, ledger x2, mean entry x2, borrowed margin x2, the pair's mean
+constexpr int kBulkStages = 2;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (unsigned spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();  // a row that never lands is a bug, not a hang
+  }
+}
 
 template <class T> __device__ __forceinline__ void gst(T* p, T v) {
   if (MDG_ST) __stcg(p, v); else *p = v;
@@ -487,7 +506,7 @@ __device__ __forceinline__ int gen_state_rows(const MdgAssetGen& g) {
 //     wave (that launch is latency-bound: a second wave would cost as much as the first);
 //   168 registers -> 3 blocks per SM, no spills: best throughput when there are many waves (>= 262,144 envs).
 // (64-thread blocks x 7 per SM at 144 registers were measured slower than either.)
-template <bool PAIRS, int BS, bool ACTIONS, bool TX2>
+template <bool PAIRS, int BS, bool ACTIONS, bool TX2, bool BULK>
 __device__ __forceinline__ void step_body(const StepArgs& a) {
   // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff (and, in the
   // all-pairs kernel, this step's normals before they are consumed; see stash_normal_row)
@@ -504,6 +523,43 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   // vectors (one per pair) that bypass L1, so that the 64 KB of unit lines per SM do not evict the prefetched state
   const bool units_v2 = MDG_UNITS_CG && PAIRS && mode == MDG_MODE_MULTI && a.units_v2;
   if (e >= N) return;
+  // Bulk staging (all-pairs kernel, whole blocks only): the nine 1-KB state rows a block needs for a pair are
+  // contiguous in the [rows][N] tensors, so one elected thread fetches them with nine cp.async.bulk copies into a
+  // two-stage shared-memory ring, two pairs ahead, completion on an mbarrier per stage.  The bytes are in flight
+  // without holding registers (the register prefetch of round 1 spilled at the 128-register budget) and arrive in
+  // shared memory instead of L2 (the prefetch.global.L1 hints still left an L2 round trip on every first use).
+  constexpr bool bulk = PAIRS && BULK;
+  double* ring = stash + 2 * na * BS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kBulkStages * kBulkRows * BS);
+  const int64_t e0 = (int64_t)blockIdx.x * BS;
+  auto bulk_issue = [&](int pp, int stage) {  // one thread
+    const uint32_t mb = smem_u32(&full[stage]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb),
+                 "r"((uint32_t)(kBulkRows * BS * sizeof(double)))
+                 : "memory");
+    const int64_t o0 = (int64_t)(2 * pp) * N + e0, o1 = o0 + N;
+    const double* src[kBulkRows] = {S.price + o0, S.price + o1, S.ledger + o0, S.ledger + o1, S.mean_entry + o0,
+                                    S.mean_entry + o1, S.borrowed + o0, S.borrowed + o1,
+                                    S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e0};
+#pragma unroll
+    for (int r = 0; r < kBulkRows; ++r)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(ring + (stage * kBulkRows + r) * BS)),
+                   "l"(src[r]), "r"((uint32_t)(BS * sizeof(double))), "r"(mb)
+                   : "memory");
+  };
+  if (bulk) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      bulk_issue(0, 0);
+      if (na > 2) bulk_issue(1, 1);
+    }
+  }
   const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
   const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;  // unused with actions
   const bool moments = shaping && (a.R.shaper == MDG_SHAPER_DSR || a.R.shaper == MDG_SHAPER_DDR);
@@ -519,7 +575,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.borrowed + o1));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e));
   };
-  if (PAIRS) {
+  if (PAIRS && !bulk) {
     // The next pair's lines are pulled into L1 with prefetch hints and loaded when needed.  (Holding the next
     // pair in registers instead made the compiler spill it at the 128-register budget -- a local store right
     // behind the load, i.e. a full-latency stall; cp.async stages in shared memory were slower too:
@@ -602,10 +658,21 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       int risk[2];
       // the pair's state arrived through the prefetch stage p & 1 (group p; at most group p+1 is still in flight)
       double mean;
+      if (bulk) {
+        const int stage = p & 1;
+        mbar_wait(&full[stage], (uint32_t)((p >> 1) & 1));
+        const double* rg = ring + stage * kBulkRows * BS + tid;
+        price[0] = rg[0]; price[1] = rg[BS]; cur[0] = rg[2 * BS]; cur[1] = rg[3 * BS];
+        mep[0] = rg[4 * BS]; mep[1] = rg[5 * BS]; bm[0] = rg[6 * BS]; bm[1] = rg[7 * BS];
+        mean = rg[8 * BS];
+        __syncthreads();  // every thread has taken its values: the stage is free for the pair after next
+        if (tid == 0 && p + kBulkStages < np) bulk_issue(p + kBulkStages, stage);
+      } else {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int64_t o = (int64_t)(2 * p + q) * N + e;
-        price[q] = S.price[o]; cur[q] = S.ledger[o]; mep[q] = S.mean_entry[o]; bm[q] = S.borrowed[o];
+        for (int q = 0; q < 2; ++q) {
+          const int64_t o = (int64_t)(2 * p + q) * N + e;
+          price[q] = S.price[o]; cur[q] = S.ledger[o]; mep[q] = S.mean_entry[o]; bm[q] = S.borrowed[o];
+        }
       }
       if (units_v2) {
         const double2 u2 = __ldcg(reinterpret_cast<const double2*>(urow + 2 * p));
@@ -621,14 +688,18 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) units[q] = action_units(arow[2 * p + q], act_half, act_scale, price[q], cur[q]);
       }
-      mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
-      if (p + MDG_PFDIST < np) prefetch_hint(p + MDG_PFDIST);
+      if (!bulk) {
+        mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
+        if (p + MDG_PFDIST < np) prefetch_hint(p + MDG_PFDIST);
+      }
+      {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int i = 2 * p + q;
-        if (mode == MDG_MODE_SINGLE) units[q] = (i == a.L.asset_idx) ? urow[0] : 0.;
-        tx_asset<TX2>(a, c, A, N, e, na, i, price[q], cur[q], mep[q], bm[q], units[q], tp[q], tu[q], tc[q], risk[q],
-                 prev_val[q]);
+        for (int q = 0; q < 2; ++q) {
+          const int i = 2 * p + q;
+          if (mode == MDG_MODE_SINGLE) units[q] = (i == a.L.asset_idx) ? urow[0] : 0.;
+          tx_asset<TX2>(a, c, A, N, e, na, i, price[q], cur[q], mep[q], bm[q], units[q], tp[q], tu[q], tc[q], risk[q],
+                        prev_val[q]);
+        }
       }
       // OUPair::getData, DataSource.cpp:1232-1240 (draw order rw, x0, x1)
       const MdgAssetGen& g0 = P.gen[2 * p];
@@ -824,9 +895,12 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   }
 }
 
-template <bool PAIRS, int BS, int MINB, bool ACTIONS>
+template <bool PAIRS, int BS, int MINB, bool ACTIONS, bool BULK = false>
 __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ StepArgs a) {
-  step_body<PAIRS, BS, ACTIONS, (MINB < 4)>(a);  // MINB 3 = the multi-wave register budget
+#ifndef MDG_BULK_TX2
+#define MDG_BULK_TX2 0
+#endif
+  step_body<PAIRS, BS, ACTIONS, (MINB < 4) || (BULK && MDG_BULK_TX2), BULK>(a);  // MINB 3 = the multi-wave register budget
 }
 
 // host side: is every asset part of an OUPair laid out (role0, role1) with in-order noise slots?
@@ -863,11 +937,33 @@ static inline int launch_step(StepArgs& a) {
   a.c_force_exact = (a.L.flags & MDG_FLAG_FORCE_EXACT_GATE) ? 1 : 0;
   const unsigned grid = (unsigned)((N + 127) / 128);
   a.units_v2 = (a.IO.units && (reinterpret_cast<uintptr_t>(a.IO.units) & 15) == 0 && a.P.n_assets % 2 == 0) ? 1 : 0;
-  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128;
-  const bool acts = a.L.mode == MDG_MODE_MULTI && (a.IO.actions || a.IO.weights);
+  static const int bulk_off = [] { const char* v = getenv("MDG_NO_BULK"); return v ? atoi(v) : 0; }();
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool small = N <= 148 * 512 * 2;  // up to two waves at 4 blocks per SM
+  // (bulk staging only in the one-wave variant: measured neutral there -- 39.3 us either way at 65,536 envs -- and
+  // 4 % slower in the multi-wave regime, where the per-pair block barrier couples the warps)
+  a.bulk = (pairs && small && !bulk_off && N % 128 == 0 && al16(a.S.price) && al16(a.S.ledger) && al16(a.S.mean_entry) &&
+            al16(a.S.borrowed) && al16(a.S.gstate)) ? 1 : 0;
+  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128 +
+                      (a.bulk ? sizeof(double) * kBulkStages * kBulkRows * 128 + 16 : 0);
+  if (smem > 48 * 1024) {  // the bulk ring lifts the all-pairs kernels above the default dynamic shared-memory limit
+    static const cudaError_t attr = [] {
+      cudaError_t e_ = cudaSuccess;
+      auto set = [&](const void* f) {
+        const cudaError_t r_ = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        if (r_ != cudaSuccess) e_ = r_;
+      };
+      set((const void*)step_kernel<true, 128, 4, true, true>); set((const void*)step_kernel<true, 128, 4, false, true>);
+      return e_;
+    }();
+    if (attr != cudaSuccess) return cuda_err(attr, "mdg_step shared-memory opt-in");
+  }
+  const bool acts = a.L.mode == MDG_MODE_MULTI && (a.IO.actions || a.IO.weights);
 #define MDG_LAUNCH(PAIRS_, MINB_, ACT_) step_kernel<PAIRS_, 128, MINB_, ACT_><<<grid, 128, smem, st>>>(a)
-  if (small) {
+  if (small && a.bulk) {
+    if (acts) step_kernel<true, 128, 4, true, true><<<grid, 128, smem, st>>>(a);
+    else step_kernel<true, 128, 4, false, true><<<grid, 128, smem, st>>>(a);
+  } else if (small) {
     if (pairs) { if (acts) MDG_LAUNCH(true, 4, true); else MDG_LAUNCH(true, 4, false); }
     else { if (acts) MDG_LAUNCH(false, 4, true); else MDG_LAUNCH(false, 4, false); }
   } else {
