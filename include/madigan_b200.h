@@ -28,10 +28,12 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 11
+#define MDG_ABI_VERSION 12
 #define MDG_MAX_ASSETS 16
 #define MDG_GEN_NPARAM 10
 #define MDG_MAX_NSTEP 64
+#define MDG_MAX_SINE_COMPONENTS 16 /* 3 random bools per component share one 53-bit uniform */
+#define MDG_MAX_SINE_TRENDS 4
 
 /* error codes (reference: C++ exceptions translated by pybind11, DataTypes.h:36-46) */
 #define MDG_OK 0
@@ -55,7 +57,10 @@ enum MdgGenType {
   MDG_GEN_TRENDYOU = 5,    /* DataSource.cpp:1602-1657 */
   MDG_GEN_SAWTOOTH = 6,    /* DataSource.cpp:558-567  */
   MDG_GEN_TRIANGLE = 7,    /* DataSource.cpp:569-578  */
-  MDG_GEN_GAUSSIAN = 8     /* DataSource.cpp:1108-1114 */
+  MDG_GEN_GAUSSIAN = 8,    /* DataSource.cpp:1108-1114 */
+  MDG_GEN_SINEADDER = 9,   /* DataSource.cpp:663-673  */
+  MDG_GEN_SINEDYNAMIC = 10,     /* DataSource.cpp:802-841 + WaveTableOsc.h */
+  MDG_GEN_SINEDYNAMICTREND = 11 /* DataSource.cpp:1002-1047 */
 };
 
 /* parameter slots p[] per generator type
@@ -66,16 +71,35 @@ enum MdgGenType {
  *  TRENDOU/TRENDYOU: 0 trendProb 1 minPeriod 2 maxPeriod 3 dYMin 4 dYMax 5 start
  *                    6 theta 7 phi 8 noiseTrend 9 emaAlpha(unused by the reference)
  *  GAUSSIAN:    0 mean 1 var(used as stddev)
+ *  SINEADDER:   0 K (components) 1 offset into MdgParams.gen_ext 2 dX 3 noise
+ *               gen_ext[off + 4c ..]: freq, mu, amp, phase of component c
+ *  SINEDYNAMIC: 0 K 1 offset into gen_ext 2 sampleRate = (int)(1/dX) 3 noise
+ *               gen_ext[off + 12c ..]: freq lo,hi,step; mu lo,hi,step; amp lo,hi,step; number of wave
+ *               tables; offset of the component's table list; 0.  Table list entry (3 doubles): topFreq,
+ *               len, offset of the len+1 samples (WaveTableOsc.h:126-157: sin(i 2 pi / len), last = first).
+ *               The host builds the samples with libm's sin, so the oracle and the kernels interpolate
+ *               the same doubles.
+ *  SINEDYNAMICTREND: as SINEDYNAMIC, plus 4 T (trends) 5 offset of the trend list in gen_ext
+ *               (4 doubles per trend: min length, max length, increment, probability)
  * generator-state rows (gstate) per asset, starting at gslot
  *  SYNTH/SAWTOOTH/TRIANGLE: x          OU/GAUSSIAN: none
  *  OUPAIR role 0: shared mean          OUPAIR role 1: none (uses partner's row)
  *  SIMPLETREND: dY, flags              TRENDOU: ouMean, dY, flags
  *  TRENDYOU: ouComponent, trendComponent, dY, flags
+ *  SINEADDER: x of each component (K rows)
+ *  SINEDYNAMIC: freq, mu, amp, phasor of each component (4K rows)
+ *  SINEDYNAMICTREND: the 4K rows, trendComponent, one flags row per trend
  *  flags (int64 stored in the double row): bit0 trending, bit1 direction(+1),
  *  bits 32..63 remaining trend length.
  * noise slots: nslot = this asset's normal draw; nslot_aux = OUPair role 0 shared
  * random-walk draw (pair order rw,x0,x1 = DataSource.cpp:1233-1235); uslot = first
  * of 4 uniform slots (trigger, direction, length, dY) for the trend generators.
+ * SINEADDER draws K normals (nslot + c).  SINEDYNAMIC(TREND) draws one normal and its random booleans
+ * (randomBoolGenerator.h:8-14; 3 per component in the order mu, amp, freq, then one direction per trend)
+ * from ONE uniform at uslot: boolean b is bit 52-b of floor(u 2^53).  SINEDYNAMICTREND then uses uslot+1+2j
+ * (trend-start test) and uslot+2+2j (trend length) for trend j.  The uniform_real draws of the constructor
+ * and of reset() (freq, mu, amp of every component, DataSource.cpp:771-773,783-787) come from Philox streams
+ * 3 and 2 at the env's current tick, slot 64*asset + 3c + {0,1,2}.
  */
 typedef struct MdgAssetGen {
   int32_t type;
@@ -101,6 +125,8 @@ typedef struct MdgParams {
   double slippage_rel, slippage_abs;
   double tcost_rel, tcost_abs;
   MdgAssetGen gen[MDG_MAX_ASSETS];
+  const double *gen_ext; /* device memory: parameter/wave tables of the SINE* generators, or NULL */
+  int64_t n_gen_ext;     /* doubles in gen_ext */
 } MdgParams;
 
 /* reward shaping (reference: utils/buffers/nstep_buffer.py:23-312,378-408 and the

@@ -5,12 +5,14 @@ checks the struct sizes against the compiled library (``mdg_sizeof``).
 """
 import ctypes as C
 
-MDG_ABI_VERSION = 11
+MDG_ABI_VERSION = 12
 FLAG_FORCE_EXACT_GATE = 1
 XFORM_NONE, XFORM_PAIR_RATIO, XFORM_RETURNS = 0, 1, 2
 MDG_MAX_ASSETS = 16
 MDG_GEN_NPARAM = 10
 MDG_MAX_NSTEP = 64
+MDG_MAX_SINE_COMPONENTS = 16
+MDG_MAX_SINE_TRENDS = 4
 MDG_STATS_NSCALAR = 8
 
 MDG_OK, MDG_E_INVALID, MDG_E_UNSUPPORTED, MDG_E_CUDA = 0, -1, -2, -3
@@ -20,6 +22,7 @@ RISK_GREEN, RISK_INSUFF_MARGIN, RISK_MARGIN_CALL, RISK_BLOWN_OUT = 0, 1, 2, 3
 
 GEN_SYNTH, GEN_OU, GEN_OUPAIR, GEN_SIMPLETREND, GEN_TRENDOU, GEN_TRENDYOU = 0, 1, 2, 3, 4, 5
 GEN_SAWTOOTH, GEN_TRIANGLE, GEN_GAUSSIAN = 6, 7, 8
+GEN_SINEADDER, GEN_SINEDYNAMIC, GEN_SINEDYNAMICTREND = 9, 10, 11
 
 SHAPER_OFF, SHAPER_SUM, SHAPER_DSR, SHAPER_DDR, SHAPER_COSINE = 0, 1, 2, 3, 4
 SHAPER_SHARPE, SHAPER_SORTINO_A, SHAPER_SORTINO_B = 5, 6, 7
@@ -47,7 +50,7 @@ class MdgParams(C.Structure):
                 ("required_margin", C.c_double), ("maintenance_margin", C.c_double),
                 ("slippage_rel", C.c_double), ("slippage_abs", C.c_double),
                 ("tcost_rel", C.c_double), ("tcost_abs", C.c_double),
-                ("gen", MdgAssetGen * MDG_MAX_ASSETS)]
+                ("gen", MdgAssetGen * MDG_MAX_ASSETS), ("gen_ext", _dp), ("n_gen_ext", C.c_int64)]
 
 
 class MdgReward(C.Structure):

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(kResetBlock) reset_kernel(const __grid_constan
     for (int c = 0; c < cnt; ++c) {  // dataSource_->reset() and the empty ledger
       const MdgAssetGen& g = P.gen[i0 + c];
       double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-      pr[c] = gen_reset(g, a.S.price[(int64_t)(i0 + c) * N + e], gs, N);
+      const CtorDraws cd = ctor_draws((uint32_t)(a.L.env_offset + e), a.L.seed, s_ts[d], 2, i0 + c);
+      pr[c] = gen_reset(g, a.S.price[(int64_t)(i0 + c) * N + e], gs, N, P.gen_ext, &cd);
       a.S.ledger[(int64_t)(i0 + c) * N + e] = 0.;
       a.S.mean_entry[(int64_t)(i0 + c) * N + e] = 0.;
       a.S.borrowed[(int64_t)(i0 + c) * N + e] = 0.;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(kResetBlock) reset_kernel(const __grid_constan
       for (int c = 0; c < cnt; ++c) {
         const MdgAssetGen& g = P.gen[i0 + c];
         double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-        pr[c] = gen_tick(g, pr[c], gs, dr, pair_mean);
+        pr[c] = gen_tick(g, pr[c], gs, dr, pair_mean, P.gen_ext);
         a.IO.pre_price[((int64_t)e * k + (k - fill + t)) * na + i0 + c] = pr[c];
         if (t == fill - 1) {  // newest row = current state, also in the ring
           a.IO.obs_price[((int64_t)a.L.head * na + i0 + c) * N + e] = pr[c];
@@ -211,13 +212,18 @@ __global__ void __launch_bounds__(kFillBlock) reset_fill_kernel(const __grid_con
     const MdgAssetGen& g0 = P.gen[i0];
     const bool is_pair = g0.type == MDG_GEN_OUPAIR;
     const int cnt = is_pair ? 2 : 1;
-    const int ngs = gen_state_rows(g0);
+    const int ngs_all = gen_state_rows(g0);
+    const bool big = ngs_all > 4;  // SINE* sources: the state stays in global memory
+    const int ngs = big ? 0 : ngs_all;
     double pr[2] = {0., 0.}, gsl[4] = {0., 0., 0., 0.};
+    double* gsg = a.S.gstate + (int64_t)(g0.gslot < 0 ? 0 : g0.gslot) * N + e;
     if (worker) {
       for (int r = 0; r < ngs; ++r) gsl[r] = a.S.gstate[(int64_t)(g0.gslot + r) * N + e];
       for (int c = 0; c < cnt; ++c) pr[c] = a.S.price[(int64_t)(i0 + c) * N + e];
       for (int c = 0; c < cnt; ++c) {  // dataSource_->reset() and the empty ledger
-        pr[c] = gen_reset(P.gen[i0 + c], pr[c], gsl, 1);
+        const CtorDraws cd = ctor_draws((uint32_t)(a.L.env_offset + e), a.L.seed, ts0, 2, i0 + c);
+        pr[c] = big ? gen_reset(P.gen[i0 + c], pr[c], gsg, N, P.gen_ext, &cd)
+                    : gen_reset(P.gen[i0 + c], pr[c], gsl, 1, P.gen_ext, &cd);
         a.S.ledger[(int64_t)(i0 + c) * N + e] = 0.;
         a.S.mean_entry[(int64_t)(i0 + c) * N + e] = 0.;
         a.S.borrowed[(int64_t)(i0 + c) * N + e] = 0.;
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(kFillBlock) reset_fill_kernel(const __grid_con
           gsl[0] = m;
         } else {
           TickDraws dr;
-          dr.N = N; dr.e = e; dr.gstride = 1;
+          dr.N = N; dr.e = e; dr.gstride = big ? N : 1;
           dr.gid = gid; dr.k0 = k0; dr.k1 = k1;
 #pragma unroll 1
           for (int t = 0; t < nt; ++t) {
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(kFillBlock) reset_fill_kernel(const __grid_con
             dr.z = zs + t * nn;
             dr.uniforms = a.IO.uniforms ? a.IO.uniforms + (int64_t)(t0 + t) * P.n_uniforms * N : nullptr;
             double pair_mean = 0.;
-            pr[0] = gen_tick(g0, pr[0], gsl, dr, pair_mean);
+            pr[0] = gen_tick(g0, pr[0], big ? gsg : gsl, dr, pair_mean, P.gen_ext);
             prow[(int64_t)(t0 + t) * na] = pr[0];
           }
         }
@@ -324,7 +330,8 @@ __global__ void __launch_bounds__(128) init_kernel(const __grid_constant__ InitA
   for (int i = 0; i < na; ++i) {
     const MdgAssetGen& g = a.P.gen[i];
     double* gs = a.S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-    a.S.price[(int64_t)i * N + e] = gen_start(g, gs, N);
+    const CtorDraws cd = ctor_draws((uint32_t)(a.L.env_offset + e), a.L.seed, 0, 3, i);
+    a.S.price[(int64_t)i * N + e] = gen_start(g, gs, N, a.P.gen_ext, &cd);
     a.S.ledger[(int64_t)i * N + e] = 0.;
     a.S.mean_entry[(int64_t)i * N + e] = 0.;
     a.S.borrowed[(int64_t)i * N + e] = 0.;
@@ -377,6 +384,22 @@ static int check_common(const MdgParams* P, const MdgLaunch* L) {
     return set_err(MDG_E_UNSUPPORTED, "n_assets must be in 1..MDG_MAX_ASSETS (thread-per-env kernels)");
   if (L->n_envs < 0) return set_err(MDG_E_INVALID, "n_envs < 0");
   if (L->n_envs > (int64_t)2147483647 * 32) return set_err(MDG_E_UNSUPPORTED, "n_envs too large");
+  for (int i = 0; i < P->n_assets; ++i) {
+    const MdgAssetGen& g = P->gen[i];
+    if (g.type < MDG_GEN_SINEADDER) continue;
+    if (g.type > MDG_GEN_SINEDYNAMICTREND) return set_err(MDG_E_INVALID, "unknown generator type");
+    const int K = (int)g.p[0];
+    const int64_t off = (int64_t)g.p[1], rec = g.type == MDG_GEN_SINEADDER ? 4 : 12;
+    if (K < 1 || K > MDG_MAX_SINE_COMPONENTS) return set_err(MDG_E_UNSUPPORTED, "sine components must be in 1..MDG_MAX_SINE_COMPONENTS");
+    if (!P->gen_ext || off < 0 || off + rec * K > P->n_gen_ext) return set_err(MDG_E_INVALID, "gen_ext is null or too short for a SINE* generator");
+    if (g.type == MDG_GEN_SINEDYNAMICTREND) {
+      const int T = (int)g.p[4];
+      const int64_t toff = (int64_t)g.p[5];
+      if (T < 0 || T > MDG_MAX_SINE_TRENDS) return set_err(MDG_E_UNSUPPORTED, "trends must be in 0..MDG_MAX_SINE_TRENDS");
+      if (toff < 0 || toff + 4 * T > P->n_gen_ext) return set_err(MDG_E_INVALID, "gen_ext too short for the trend list");
+    }
+    if (g.type != MDG_GEN_SINEADDER && !(g.p[2] >= 1.)) return set_err(MDG_E_INVALID, "sampleRate must be >= 1");
+  }
   return MDG_OK;
 }
 
@@ -462,6 +485,10 @@ static int fill_ws_args(ResetWsArgs& a, const MdgParams* P, const MdgState* S, c
   a.ticket = (int*)workspace + 1;
   a.list = (int*)((char*)workspace + 256);
   a.chunk = fill_ticks < 64 ? fill_ticks : 64;
+  if (P->n_normals > 64) {  // many SineAdder components: keep the normals chunk within 32 KB of shared memory
+    const int cap = 4096 / P->n_normals;
+    a.chunk = a.chunk < cap ? a.chunk : (cap > 0 ? cap : 1);
+  }
   a.n_groups = fill_groups(*P, a.leader);
   return MDG_OK;
 }

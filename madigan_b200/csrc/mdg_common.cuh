@@ -121,6 +121,59 @@ __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b 
 __device__ __forceinline__ int u_int(double u, double a, double b) { return (int)(a + floor(u * (b - a + 1.))); }
 __device__ __forceinline__ double u_real(double u, double a, double b) { return a + u * (b - a); }
 
+// uniform draws of the SINEDYNAMIC* constructor (stream 3) and reset() (stream 2): slot 64*asset + 3c + {0,1,2}
+struct CtorDraws {
+  uint32_t gid, k0, k1, t_lo, t_hi;
+  int stream;
+  int asset;
+};
+static __device__ __noinline__ double draw_ctor_uniform(const CtorDraws& c, int slot) {
+  uint64_t x0, x1;
+  philox4x32_10(c.gid, ((uint32_t)c.stream << 16) | (uint32_t)(slot >> 1), c.t_lo, c.t_hi, c.k0, c.k1, x0, x1);
+  return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
+}
+__device__ __forceinline__ CtorDraws ctor_draws(uint32_t gid, uint64_t seed, long long tick, int stream, int asset) {
+  CtorDraws c;
+  c.gid = gid; c.k0 = (uint32_t)seed; c.k1 = (uint32_t)(seed >> 32);
+  c.t_lo = (uint32_t)(unsigned long long)tick; c.t_hi = (uint32_t)((unsigned long long)tick >> 32);
+  c.stream = stream; c.asset = asset;
+  return c;
+}
+// freq, mu, amp of every component ~ uniform_real(lo, hi) (DataSource.cpp:771-773 / 783-787, :972-974 / 992-996)
+static __device__ __noinline__ void sine_dynamic_sample(const MdgAssetGen& g, double* __restrict__ gs, int64_t N,
+                                                        const double* __restrict__ ext, const CtorDraws& c) {
+  const int K = (int)g.p[0];
+  const double* cp = ext + (int64_t)g.p[1];
+  for (int i = 0; i < K; ++i, cp += 12)
+    for (int j = 0; j < 3; ++j)
+      gs[(int64_t)(4 * i + j) * N] = u_real(draw_ctor_uniform(c, 64 * c.asset + 3 * i + j), cp[3 * j], cp[3 * j + 1]);
+}
+
+// random boolean b of this tick (randomBoolGenerator.h:8-14): bit 52-b of floor(u 2^53)
+__device__ __forceinline__ bool u_bool(unsigned long long bits, int b) { return (bits >> (52 - b)) & 1ull; }
+__device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }  // std::min
+// bounded +-step walk of updateParams (DataSource.cpp:804-812)
+__device__ __forceinline__ double sine_walk(double v, bool up, const double* r) {
+  return dmax(r[0], dmin(r[1], v + (up ? r[2] : -r[2])));
+}
+// WaveTableOsc::setFreq + process (WaveTableOsc.h:77-110) of the component with record cp
+__device__ __forceinline__ double osc_process(const double* __restrict__ ext, const double* __restrict__ cp,
+                                              double incr, double& phasor) {
+  const int nt = (int)cp[9];
+  const double* tl = ext + (int64_t)cp[10];
+  int idx = 0;
+  while (incr >= tl[3 * idx] && idx < nt - 1) ++idx;
+  phasor += incr;
+  if (phasor >= 1.) phasor -= 1.;
+  const int len = (int)tl[3 * idx + 1];
+  const double* tab = ext + (int64_t)tl[3 * idx + 2];
+  const double temp = phasor * len;
+  const int ip = (int)temp;
+  const double frac = temp - ip;
+  const double s0 = tab[ip], s1 = tab[ip + 1];
+  return s0 + (s1 - s0) * frac;
+}
+
 // One getData() of asset i (DataSource.cpp).  `price` is the asset's current price
 // (== generator value for every synthetic source), gs points at gstate row gslot for
 // this env (stride N), pair_mean carries OUPair's shared mean from role 0 to role 1.
@@ -128,7 +181,7 @@ __device__ __forceinline__ double u_real(double u, double a, double b) { return 
 // D provides N, draw_normal(d, slot), draw_uniform(d, slot).
 template <class D>
 static __device__ __noinline__ double gen_tick(const MdgAssetGen& g, double price, double* __restrict__ gs,
-                                               D& d, double& pair_mean) {
+                                               D& d, double& pair_mean, const double* __restrict__ ext = nullptr) {
   const double* p = g.p;
   const int64_t N = d.gstride;  // distance between this asset's generator-state rows
   switch (g.type) {
@@ -251,14 +304,79 @@ static __device__ __noinline__ double gen_tick(const MdgAssetGen& g, double pric
       gs[3 * N] = pack_flags(trending, dir, len);
       break;
     }
+    case MDG_GEN_SINEADDER: {  // :663-673
+      const int K = (int)p[0];
+      const double* cp = ext + (int64_t)p[1];
+      double sum = 0.;
+      for (int i = 0; i < K; ++i, cp += 4) {
+        const double x = gs[(int64_t)i * N];
+        sum = sum + ((draw_normal(d, g.nslot + i) * p[3] + cp[1]) + cp[2] * sin(MDG_PI2 * x * cp[0]));
+        gs[(int64_t)i * N] = x + p[2];
+      }
+      price = sum;
+      break;
+    }
+    case MDG_GEN_SINEDYNAMIC:
+    case MDG_GEN_SINEDYNAMICTREND: {  // :802-841, :1002-1047
+      const bool trend = g.type == MDG_GEN_SINEDYNAMICTREND;
+      const int K = (int)p[0];
+      const double* cp = ext + (int64_t)p[1];
+      const unsigned long long bits = (unsigned long long)(draw_uniform(d, g.uslot) * 0x1.0p53);
+      double tcmp = trend ? gs[(int64_t)(4 * K) * N] : 1.;
+      double sum = 0.;
+      for (int i = 0; i < K; ++i, cp += 12) {
+        double* s = gs + (int64_t)(4 * i) * N;
+        const double mu = sine_walk(s[N], u_bool(bits, 3 * i), cp + 3);
+        const double amp = sine_walk(s[2 * N], u_bool(bits, 3 * i + 1), cp + 6);
+        const double freq = sine_walk(s[0], u_bool(bits, 3 * i + 2), cp);
+        double phasor = s[3 * N];
+        const double o = osc_process(ext, cp, freq / p[2], phasor);
+        s[0] = freq; s[N] = mu; s[2 * N] = amp; s[3 * N] = phasor;
+        sum = trend ? sum + tcmp * (mu + amp * o) : sum + (mu + amp * o);
+      }
+      const double z = draw_normal(d, g.nslot) * p[3] + 0.;
+      if (!trend) {
+        price = sum + z;
+        break;
+      }
+      const int T = (int)p[4];
+      const double* tp = ext + (int64_t)p[5];
+      for (int j = 0; j < T; ++j, tp += 4) {
+        double* fl = gs + (int64_t)(4 * K + 1 + j) * N;
+        int trending, dir, len;
+        unpack_flags(fl[0], trending, dir, len);
+        if (trending) {
+          tcmp += tcmp * tp[2] * dir;
+          if (--len == 0) trending = 0;
+        } else {
+          const double r = draw_uniform(d, g.uslot + 1 + 2 * j);
+          if (r < tp[3]) {
+            trending = 1;
+            dir = u_bool(bits, 3 * K + j) ? -1 : 1;
+            len = u_int(draw_uniform(d, g.uslot + 2 + 2 * j), tp[0], tp[1]);
+          }
+        }
+        if (tcmp <= .1) dir = 1;
+        tcmp = dmax(0.01, tcmp);
+        fl[0] = pack_flags(trending, dir, len);
+      }
+      gs[(int64_t)(4 * K) * N] = tcmp;
+      price = sum + tcmp + tcmp * z;
+      break;
+    }
   }
   return price;
 }
 
 // DataSource::reset() of asset i; returns the new price (Synth/OU/Gaussian: unchanged).
 __device__ __forceinline__ double gen_reset(const MdgAssetGen& g, double price, double* __restrict__ gs,
-                                            int64_t N) {
+                                            int64_t N, const double* __restrict__ ext = nullptr,
+                                            const CtorDraws* cd = nullptr) {
   switch (g.type) {
+    case MDG_GEN_SINEDYNAMIC:
+    case MDG_GEN_SINEDYNAMICTREND:  // :783-787, :992-996: new freq, mu, amp; phasors and trend state stay
+      sine_dynamic_sample(g, gs, N, ext, *cd);
+      return price;
     case MDG_GEN_OUPAIR:  // DataSource.cpp:1242-1246
       if (g.role == 0) gs[0] = 10.;
       return 10.;
@@ -286,8 +404,27 @@ __device__ __forceinline__ double gen_reset(const MdgAssetGen& g, double price, 
 }
 
 // constructor state of asset i (initParams of each source); returns the start price
-__device__ __forceinline__ double gen_start(const MdgAssetGen& g, double* __restrict__ gs, int64_t N) {
+__device__ __forceinline__ double gen_start(const MdgAssetGen& g, double* __restrict__ gs, int64_t N,
+                                            const double* __restrict__ ext = nullptr, const CtorDraws* cd = nullptr) {
   switch (g.type) {
+    case MDG_GEN_SINEADDER: {  // x = phase, DataSource.cpp:652
+      const int K = (int)g.p[0];
+      const double* cp = ext + (int64_t)g.p[1];
+      for (int i = 0; i < K; ++i) gs[(int64_t)i * N] = cp[4 * i + 3];
+      return 0.;
+    }
+    case MDG_GEN_SINEDYNAMIC:
+    case MDG_GEN_SINEDYNAMICTREND: {  // :741-780, :938-989
+      const int K = (int)g.p[0];
+      sine_dynamic_sample(g, gs, N, ext, *cd);
+      for (int i = 0; i < K; ++i) gs[(int64_t)(4 * i + 3) * N] = 0.;  // phasor, WaveTableOsc.h:62
+      if (g.type == MDG_GEN_SINEDYNAMICTREND) {
+        const int T = (int)g.p[4];
+        gs[(int64_t)(4 * K) * N] = 1.;  // trendComponent :982
+        for (int j = 0; j < T; ++j) gs[(int64_t)(4 * K + 1 + j) * N] = pack_flags(0, 1, 0);
+      }
+      return 0.;
+    }
     case MDG_GEN_SYNTH:
     case MDG_GEN_SAWTOOTH:
     case MDG_GEN_TRIANGLE:

@@ -123,7 +123,15 @@ static __device__ __noinline__ double shaper_pop(const MdgReward& R, const NStep
     case MDG_SHAPER_SUM:
     case MDG_SHAPER_COSINE: {  // :23-27, :182-204
       double s = 0.;
-      for (int j = 0; j < n; ++j) s = s + disc[j] * v.at(first + j);
+      for (int j = 0; j < n; j += 4) {  // four ring loads in flight, summed in entry order
+        const int m = n - j;
+        const double x0 = v.at(first + j), x1 = m > 1 ? v.at(first + j + 1) : 0.,
+                     x2 = m > 2 ? v.at(first + j + 2) : 0., x3 = m > 3 ? v.at(first + j + 3) : 0.;
+        s = s + disc[j] * x0;
+        if (m > 1) s = s + disc[j + 1] * x1;
+        if (m > 2) s = s + disc[j + 2] * x2;
+        if (m > 3) s = s + disc[j + 3] * x3;
+      }
       return s;
     }
     case MDG_SHAPER_DSR: {  // :62-78
@@ -497,6 +505,9 @@ __device__ __forceinline__ int gen_state_rows(const MdgAssetGen& g) {
     case MDG_GEN_TRENDYOU: return 4;
     case MDG_GEN_TRENDOU: return 3;
     case MDG_GEN_SIMPLETREND: return 2;
+    case MDG_GEN_SINEADDER: return (int)g.p[0];
+    case MDG_GEN_SINEDYNAMIC: return 4 * (int)g.p[0];
+    case MDG_GEN_SINEDYNAMICTREND: return 4 * (int)g.p[0] + 1 + (int)g.p[4];
     default: return 1;
   }
 }
@@ -759,7 +770,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
         newp = price + ((g.p[1] * (g.p[0] - price)) + g.p[0] * g.p[2] * draw_normal(dr, g.nslot));
       } else {
         double* gs = S.gstate + (int64_t)(g.gslot < 0 ? 0 : g.gslot) * N + e;
-        newp = gen_tick(g, price, gs, dr, pair_mean);
+        newp = gen_tick(g, price, gs, dr, pair_mean, P.gen_ext);
       }
       post_tick<false, BS>(a, A, N, e, na, i, cur, newp, prev_val, tp, tu, tc, st);
     }

@@ -13,6 +13,8 @@ Deviations, all listed in SURVEY.md Appendix A:
 """
 import math
 
+import numpy as np
+
 from .. import _abi as A
 
 
@@ -35,6 +37,15 @@ _DEFAULTS = {
                     dYMin=[0.001, 0.01], dYMax=[0.003, 0.03], start=[10., 15.], theta=[1., 0.5],
                     phi=[2., 2.1], noise_trend=[1., 1.2], ema_alpha=[0.1, 0.2]),
 }
+_DEFAULTS["SineAdder"] = _DEFAULTS["Synth"]  # DataSource.cpp:581-588 (one asset, four components)
+# DataSource.cpp:677-687, :850-862.  The reference's default constructors pass the still-zero member dX, so
+# sampleRate = (int)(1/0); its config fallback uses dX = 0.01, which is what these defaults use (noise 1).
+_DEFAULTS["SineDynamic"] = dict(freqRange=[[.1, 1., .01], [0.3, 3.0, .01], [5., 15., .1], [10., 50., .1]],
+                                muRange=[[1., 5., .02], [.3, 3., .05], [.2, 5., .02], [.5, 5., .02]],
+                                ampRange=[[1., 5., .01], [.3, 3., .02], [.2, 2., .04], [.5, 5., .05]],
+                                dX=0.01, noise=1.)
+_DEFAULTS["SineDynamicTrend"] = dict(_DEFAULTS["SineDynamic"], trendRange=[[100, 500], [100, 300]],
+                                     trendIncr=[0.1, 0.2], trendProb=[.001, .01])
 _DEFAULTS["SawTooth"] = _DEFAULTS["Synth"]
 _DEFAULTS["Triangle"] = _DEFAULTS["Synth"]
 _DEFAULTS["TrendyOU"] = _DEFAULTS["TrendOU"]
@@ -72,18 +83,28 @@ class _Table:
         self.n_gstate = 0
         self.n_normals = 0
         self.n_uniforms = 0
+        self.ext = []      # MdgParams.gen_ext: parameter / wave tables of the SINE* generators
+        self._wave = {}    # table length -> offset of its samples in ext
 
-    def add(self, name, type_, p, n_g, role=0, aux_normal=False, uniforms=False, partner=-1):
+    def wave_table(self, length):
+        """offset of sin(i 2 pi / length), i = 0..length (last = first), WaveTableOsc.h:113-157"""
+        if length not in self._wave:
+            self._wave[length] = len(self.ext)
+            tab = [math.sin(float(i) * 2. * math.pi / length) for i in range(length)]  # libm sin, as the reference
+            self.ext.extend(tab + tab[:1])
+        return self._wave[length]
+
+    def add(self, name, type_, p, n_g, role=0, aux_normal=False, uniforms=False, partner=-1, normals=1):
         rec = dict(type=type_, role=role, nslot=-1, nslot_aux=-1, uslot=-1, gslot=-1,
                    partner=partner, p=list(p) + [0.] * (A.MDG_GEN_NPARAM - len(p)))
         if aux_normal:
             rec["nslot_aux"] = self.n_normals
             self.n_normals += 1
         rec["nslot"] = self.n_normals
-        self.n_normals += 1
+        self.n_normals += normals
         if uniforms:
             rec["uslot"] = self.n_uniforms
-            self.n_uniforms += 4
+            self.n_uniforms += 4 if uniforms is True else int(uniforms)
         if n_g:
             rec["gslot"] = self.n_gstate
             self.n_gstate += n_g
@@ -133,13 +154,98 @@ def _add_source(tab, kind, cfg):
         t, ng = (A.GEN_TRENDOU, 3) if kind == "TrendOU" else (A.GEN_TRENDYOU, 4)
         for i in range(_same_len(kind, *v)):
             tab.add(f"{kind}_{i}", t, [x[i] for x in v], ng, uniforms=True)
+    elif kind == "SineAdder":  # :590-661: ONE asset, the sum of the components
+        freq, mu, amp, phase = (_vec(cfg, k) for k in ("freq", "mu", "amp", "phase"))
+        K = _same_len(kind, freq, mu, amp, phase)
+        _check_components(kind, K)
+        off = len(tab.ext)
+        for c in range(K):
+            tab.ext.extend([freq[c], mu[c], amp[c], phase[c]])
+        tab.add("multi_sine", A.GEN_SINEADDER, [K, off, float(_get(cfg, "dX")), float(cfg.get("noise", 0.))], K,
+                normals=K)
+    elif kind in ("SineDynamic", "SineDynamicTrend"):  # :689-780, :864-989
+        _add_sine_dynamic(tab, kind, cfg)
     else:
         # NotImplemented is a std::logic_error -> RuntimeError (DataSource.cpp:101-107)
         raise NotImplementedError(f"Constructor from config for {kind} as dataSource is not implemented")
 
 
-def build_generator_table(data_source_type, data_source_config=None):
-    """Returns (asset_names, list-of-asset-records, n_gstate, n_normals, n_uniforms)."""
+def _check_components(kind, K):
+    if not 1 <= K <= A.MDG_MAX_SINE_COMPONENTS:
+        raise ValueError(f"{kind}: {K} components, supported 1..{A.MDG_MAX_SINE_COMPONENTS}")
+
+
+def _ranges(cfg, key, width, cast=float):
+    v = _get(cfg, key)
+    out = [[cast(x) for x in row] for row in v]
+    if any(len(r) != width for r in out):
+        raise ValueError(f"{key}: every entry needs {width} values")
+    return out
+
+
+def _add_sine_dynamic(tab, kind, cfg):
+    """SineDynamic / SineDynamicTrend::initParams (DataSource.cpp:741-780, :938-989) and setSineOsc
+    (WaveTableOsc.h:126-157): per component the (lo, hi, step) ranges and the list of wave tables."""
+    trend = kind == "SineDynamicTrend"
+    fr, mr, ar = (_ranges(cfg, k, 3) for k in ("freqRange", "muRange", "ampRange"))
+    K = _same_len(kind, fr, mr, ar)
+    _check_components(kind, K)
+    dX = float(_get(cfg, "dX"))
+    noise = float(_get(cfg, "noise") if trend else cfg.get("noise", 0.))
+    if not dX > 0.:
+        raise ValueError(f"{kind}: dX must be > 0")
+    sample_rate = int(1. / dX)
+    recs = []
+    for c in range(K):
+        lo, hi = fr[c][0], fr[c][1]
+        if hi * 2 > sample_rate:  # std::logic_error -> RuntimeError (:758-765)
+            raise RuntimeError("Sampling Rate as determined by 1 / dX must be at least the nyquist sampling rate "
+                               f"relative to the largest frequency. freqRange entry #{c} with range of {lo} - {hi} "
+                               "doesn't satisfy this constraint.")
+        if not lo > 0.:
+            raise ValueError(f"{kind}: freqRange low must be > 0")
+        max_harms = int(sample_rate / (3.0 * lo) + 0.5)
+        if max_harms < 1:
+            raise ValueError(f"{kind}: freqRange low {lo} too high for sampleRate {sample_rate} (no wave table)")
+        v = 1 << (max_harms - 1).bit_length()  # next power of two
+        table_len, top = v * 2 * 2, lo * 2. / sample_rate  # overSample = 2
+        tables = []
+        while max_harms >= 1:
+            tables.append((top, table_len))
+            if table_len > 99999:  # constantRatioLimit
+                table_len >>= 1
+            top *= 2
+            max_harms >>= 1
+        tables = tables[:32]  # WaveTableOsc's default maxWaveTables (the oscillators are default-constructed, :756)
+        recs.append(tables)
+    # layout: [K component records of 12][per component: table list of 3 per table][trend list][samples ...]
+    off = len(tab.ext)
+    tab.ext.extend([0.] * (12 * K))
+    for c in range(K):
+        tl_off = len(tab.ext)
+        tab.ext.extend([0.] * (3 * len(recs[c])))
+        for t, (top, ln) in enumerate(recs[c]):
+            tab.ext[tl_off + 3 * t: tl_off + 3 * t + 3] = [top, float(ln), float(tab.wave_table(ln))]
+        tab.ext[off + 12 * c: off + 12 * c + 12] = fr[c] + mr[c] + ar[c] + [float(len(recs[c])), float(tl_off), 0.]
+    p = [K, off, float(sample_rate), noise]
+    n_g, n_u = 4 * K, 1
+    if trend:
+        tr = _ranges(cfg, "trendRange", 2, int)
+        incr, prob = _vec(cfg, "trendIncr"), _vec(cfg, "trendProb")
+        T = _same_len(kind, tr, incr, prob)
+        if T > A.MDG_MAX_SINE_TRENDS:
+            raise ValueError(f"{kind}: {T} trends, supported 0..{A.MDG_MAX_SINE_TRENDS}")
+        t_off = len(tab.ext)
+        for j in range(T):
+            tab.ext.extend([float(tr[j][0]), float(tr[j][1]), incr[j], prob[j]])
+        p += [T, t_off]
+        n_g, n_u = 4 * K + 1 + T, 1 + 2 * T
+    tab.add("sine_dynamic_trend" if trend else "sine_dynamic",
+            A.GEN_SINEDYNAMICTREND if trend else A.GEN_SINEDYNAMIC, p, n_g, uniforms=n_u)
+
+
+def build_generator_table(data_source_type, data_source_config=None, with_ext=False):
+    """Returns (asset_names, list-of-asset-records, n_gstate, n_normals, n_uniforms[, gen_ext list])."""
     tab = _Table()
     if data_source_type == "Composite":  # DataSource.cpp:411-437, Config.cpp:107-126
         if not data_source_config:
@@ -158,15 +264,19 @@ def build_generator_table(data_source_type, data_source_config=None):
     if len(tab.assets) > A.MDG_MAX_ASSETS:
         raise ValueError(f"{len(tab.assets)} assets > MDG_MAX_ASSETS={A.MDG_MAX_ASSETS} "
                          "(thread-per-env kernels keep the whole portfolio in registers)")
-    return tab.names, tab.assets, tab.n_gstate, tab.n_normals, tab.n_uniforms
+    out = (tab.names, tab.assets, tab.n_gstate, tab.n_normals, tab.n_uniforms)
+    return out + (tab.ext,) if with_ext else out
 
 
 def make_params(data_source_type, data_source_config=None, init_cash=1_000_000.,
                 required_margin=0., maintenance_margin=0., slippage_rel=0., slippage_abs=0.,
                 transaction_cost_rel=0., transaction_cost_abs=0.):
     """Fill an ``MdgParams``.  Margin/cost defaults are Env's (0, Env.h:131-136), not Portfolio's."""
-    names, assets, n_g, n_n, n_u = build_generator_table(data_source_type, data_source_config)
+    names, assets, n_g, n_n, n_u, ext = build_generator_table(data_source_type, data_source_config, with_ext=True)
     P = A.MdgParams()
+    # SINE* sources: parameter / wave tables.  gen_ext (a DEVICE pointer) is set by the env after the upload.
+    P.ext_host = np.asarray(ext, dtype=np.float64) if ext else None
+    P.gen_ext, P.n_gen_ext = None, len(ext)
     P.n_assets, P.n_gstate, P.n_normals, P.n_uniforms = len(assets), n_g, n_n, n_u
     P.init_cash = float(init_cash)
     P.required_margin = float(required_margin)

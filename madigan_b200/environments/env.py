@@ -116,6 +116,9 @@ class Env:
         self._initCash = float(initCash)
         self.P, self._asset_names = make_params(dataSourceType, ds_cfg, init_cash=initCash)
         self.nA = self.P.n_assets
+        if self.P.ext_host is not None:  # SINE* sources: parameter / wave tables in device memory
+            self._gen_ext = torch.from_numpy(self.P.ext_host).to(self.device)
+            self.P.gen_ext, self.P.n_gen_ext = self._gen_ext.data_ptr(), self._gen_ext.numel()
         if reward is None and _cfg_get(config, "reward_shaper_config") is not None and _cfg_get(config, "in_kernel_rewards", False):
             ac = _cfg_get(config, "agent_config")
             reward = dict(reward_shaper_config=_cfg_get(config, "reward_shaper_config"),

@@ -31,6 +31,7 @@
 #include "mdg_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -84,6 +85,15 @@ double orc_draw_uniform(uint64_t seed, int64_t gid, int64_t tick, int slot) {
   return (double)(((slot & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
 }
 
+/* uniform draws of the SINEDYNAMIC* constructor (stream 3) and reset() (stream 2) */
+static double ctor_uniform(const OrcEnv *e, int stream, int asset, int slot) {
+  if (e->n_ctor_u > 0) return e->ctor_u[slot];
+  uint64_t x0, x1;
+  int s = 64 * asset + slot;
+  philox_block(e->seed, e->gid, e->timestamp, stream, s >> 1, &x0, &x1);
+  return (double)(((s & 1) ? x1 : x0) >> 11) * 0x1.0p-53;
+}
+
 typedef struct Draws {
   const OrcEnv *e;
   const double *normals;
@@ -108,6 +118,18 @@ static inline double bits_dbl(int64_t b) { double x; memcpy(&x, &b, 8); return x
 static inline int64_t pack_flags(int trending, int dir, int32_t len) {
   return (int64_t)(trending ? FLAG_TRENDING : 0) | (int64_t)(dir > 0 ? FLAG_DIRPOS : 0) |
          (int64_t)((uint64_t)(uint32_t)len << 32);
+}
+
+static inline double u_real(double u, double a, double b);
+/* freq, mu, amp of every component ~ uniform_real(lo, hi): DataSource.cpp:771-773 / 783-787, :972-974 / 992-996 */
+static void sine_dynamic_sample(OrcEnv *e, int i, int stream) {
+  const MdgAssetGen *g = &e->P.gen[i];
+  double *gs = &e->gstate[g->gslot];
+  const int K = (int)g->p[0];
+  const double *cp = e->P.gen_ext + (int64_t)g->p[1];
+  for (int c = 0; c < K; ++c, cp += 12)
+    for (int j = 0; j < 3; ++j)
+      gs[4 * c + j] = u_real(ctor_uniform(e, stream, i, 3 * c + j), cp[3 * j], cp[3 * j + 1]);
 }
 
 static void gen_start(OrcEnv *e) {
@@ -145,6 +167,25 @@ static void gen_start(OrcEnv *e) {
         gs[2] = 0.;
         gs[3] = bits_dbl(pack_flags(0, 1, 0));
         break;
+      case MDG_GEN_SINEADDER: { /* x = phase, DataSource.cpp:652; currentData_ resized only */
+        const int K = (int)g->p[0];
+        const double *cp = P->gen_ext + (int64_t)g->p[1];
+        for (int c = 0; c < K; ++c) gs[c] = cp[4 * c + 3];
+        e->price[i] = 0.;
+        break;
+      }
+      case MDG_GEN_SINEDYNAMIC: case MDG_GEN_SINEDYNAMICTREND: { /* :741-780, :938-989 */
+        const int K = (int)g->p[0];
+        sine_dynamic_sample(e, i, 3);
+        for (int c = 0; c < K; ++c) gs[4 * c + 3] = 0.; /* phasor, WaveTableOsc.h:62 */
+        if (g->type == MDG_GEN_SINEDYNAMICTREND) {
+          const int T = (int)g->p[4];
+          gs[4 * K] = 1.; /* trendComponent :982 */
+          for (int j = 0; j < T; ++j) gs[4 * K + 1 + j] = bits_dbl(pack_flags(0, 1, 0)); /* :983-988 */
+        }
+        e->price[i] = 0.;
+        break;
+      }
     }
   }
 }
@@ -179,6 +220,10 @@ static void gen_reset(OrcEnv *e) {
         gs[3] = bits_dbl(pack_flags(0, (f & FLAG_DIRPOS) ? 1 : -1, 0));
         break;
       }
+      case MDG_GEN_SINEDYNAMIC: case MDG_GEN_SINEDYNAMICTREND:
+        /* :783-787, :992-996: new freq, mu, amp; the oscillators' phase and the trend state are kept */
+        sine_dynamic_sample(e, i, 2);
+        break;
       default: break;
     }
   }
@@ -189,6 +234,29 @@ static inline double dmax(double a, double b) { return (a < b) ? b : a; } /* std
 /* uniform_int_distribution(a,b) and uniform_real_distribution(a,b) from one u in [0,1) */
 static inline int32_t u_int(double u, double a, double b) { return (int32_t)(a + floor(u * (b - a + 1.))); }
 static inline double u_real(double u, double a, double b) { return a + u * (b - a); }
+static inline double dmin(double a, double b) { return (b < a) ? b : a; } /* std::min */
+/* random boolean b of this tick (randomBoolGenerator.h:8-14): bit 52-b of floor(u 2^53) */
+static inline int u_bool(uint64_t bits, int b) { return (int)((bits >> (52 - b)) & 1u); }
+/* bounded +-step walk of updateParams (DataSource.cpp:804-812) */
+static inline double sine_walk(double v, int up, const double *r) {
+  return dmax(r[0], dmin(r[1], v + (up ? r[2] : -r[2])));
+}
+/* WaveTableOsc::setFreq + process (WaveTableOsc.h:77-110) of the component with record cp */
+static double osc_process(const double *ext, const double *cp, double incr, double *phasor) {
+  const int nt = (int)cp[9];
+  const double *tl = ext + (int64_t)cp[10];
+  int idx = 0;
+  while (incr >= tl[3 * idx] && idx < nt - 1) ++idx; /* setFreq :80-85 */
+  *phasor += incr;                                   /* updatePhase :39 */
+  if (*phasor >= 1.) *phasor -= 1.;
+  const int len = (int)tl[3 * idx + 1];              /* getOutput :89-101 */
+  const double *tab = ext + (int64_t)tl[3 * idx + 2];
+  const double temp = *phasor * len;
+  const int ip = (int)temp;
+  const double frac = temp - ip;
+  const double s0 = tab[ip], s1 = tab[ip + 1];
+  return s0 + (s1 - s0) * frac;
+}
 
 void orc_tick(OrcEnv *e, const double *normals, const double *uniforms) {
   const MdgParams *P = &e->P;
@@ -312,6 +380,60 @@ void orc_tick(OrcEnv *e, const double *normals, const double *uniforms) {
         gs[0] = ou; gs[1] = tr;
         e->price[i] = ou + tr;
         gs[3] = bits_dbl(pack_flags(trending, dir, len));
+        break;
+      }
+      case MDG_GEN_SINEADDER: { /* :663-673 */
+        const int K = (int)p[0];
+        const double *cp = P->gen_ext + (int64_t)p[1];
+        double sum = 0.;
+        for (int c = 0; c < K; ++c, cp += 4) {
+          double x = gs[c];
+          sum = sum + ((dn(&d, g->nslot + c) * p[3] + cp[1]) + cp[2] * sin(PI2 * x * cp[0]));
+          gs[c] = x + p[2];
+        }
+        e->price[i] = sum;
+        break;
+      }
+      case MDG_GEN_SINEDYNAMIC: case MDG_GEN_SINEDYNAMICTREND: { /* :802-841, :1002-1047 */
+        const int trend = g->type == MDG_GEN_SINEDYNAMICTREND;
+        const int K = (int)p[0];
+        const double *ext = P->gen_ext, *cp = ext + (int64_t)p[1];
+        const uint64_t bits = (uint64_t)(du(&d, g->uslot) * 0x1.0p53);
+        double tcmp = trend ? gs[4 * K] : 1.;
+        double sum = 0.;
+        for (int c = 0; c < K; ++c, cp += 12) { /* updateParams (:802-815) then the component sum (:833-838) */
+          double *s = gs + 4 * c;
+          s[1] = sine_walk(s[1], u_bool(bits, 3 * c), cp + 3);
+          s[2] = sine_walk(s[2], u_bool(bits, 3 * c + 1), cp + 6);
+          s[0] = sine_walk(s[0], u_bool(bits, 3 * c + 2), cp);
+          double o = osc_process(ext, cp, s[0] / p[2], &s[3]);
+          sum = trend ? sum + tcmp * (s[1] + s[2] * o) : sum + (s[1] + s[2] * o);
+        }
+        double z = dn(&d, g->nslot) * p[3] + 0.; /* normal_distribution(0, noise) */
+        if (!trend) { e->price[i] = sum + z; break; }
+        const int T = (int)p[4];
+        const double *tp = ext + (int64_t)p[5];
+        for (int j = 0; j < T; ++j, tp += 4) { /* :1021-1040 */
+          int64_t f = dbl_bits(gs[4 * K + 1 + j]);
+          int trending = (int)(f & FLAG_TRENDING), dir = (f & FLAG_DIRPOS) ? 1 : -1;
+          int32_t len = (int32_t)((uint64_t)f >> 32);
+          if (trending) {
+            tcmp += tcmp * tp[2] * dir;
+            if (--len == 0) trending = 0;
+          } else {
+            double r = du(&d, g->uslot + 1 + 2 * j);
+            if (r < tp[3]) {
+              trending = 1;
+              dir = u_bool(bits, 3 * K + j) ? -1 : 1;
+              len = u_int(du(&d, g->uslot + 2 + 2 * j), tp[0], tp[1]);
+            }
+          }
+          if (tcmp <= .1) dir = 1;
+          tcmp = dmax(0.01, tcmp);
+          gs[4 * K + 1 + j] = bits_dbl(pack_flags(trending, dir, len));
+        }
+        gs[4 * K] = tcmp;
+        e->price[i] = sum + tcmp + tcmp * z; /* :1041 */
         break;
       }
     }
@@ -615,8 +737,23 @@ void orc_shaper_feed(OrcEnv *e, const double *raw, int ra, const double *port, i
 /* ------------------------------------------------------------------ */
 /* Env  (environments/cpp/Env.h)                                        */
 /* ------------------------------------------------------------------ */
+void orc_set_ctor_uniforms(OrcEnv *e, const double *u, int n) {
+  e->n_ctor_u = (u && n > 0) ? (n > ORC_MAX_CTOR_U ? ORC_MAX_CTOR_U : n) : 0;
+  for (int i = 0; i < e->n_ctor_u; ++i) e->ctor_u[i] = u[i];
+}
+
 void orc_init(OrcEnv *e, const MdgParams *P, const MdgReward *R, uint64_t seed, int64_t gid) {
+  orc_init_inject(e, P, R, seed, gid, 0, 0);
+}
+
+void orc_init_inject(OrcEnv *e, const MdgParams *P, const MdgReward *R, uint64_t seed, int64_t gid,
+                     const double *ctor_u, int n_ctor_u) {
   memset(e, 0, sizeof(*e));
+  if (P->n_gstate > ORC_MAX_GSTATE) {
+    fprintf(stderr, "mdg_oracle: n_gstate %d > ORC_MAX_GSTATE %d\n", P->n_gstate, ORC_MAX_GSTATE);
+    abort();
+  }
+  orc_set_ctor_uniforms(e, ctor_u, n_ctor_u);
   e->P = *P;
   if (R) e->R = *R; else { e->R.shaper = MDG_SHAPER_OFF; e->R.nstep = 1; }
   e->seed = seed;
@@ -790,7 +927,7 @@ void orc_batch_step(OrcBatch *b, const MdgStepIO *io, const MdgLaunch *L, int th
   for (int64_t i = 0; i < N; ++i) {
     OrcEnv *e = &b->envs[i];
     const int nA = e->P.n_assets;
-    double nz[64], uz[64], un[MDG_MAX_ASSETS];
+    double nz[16 * MDG_MAX_SINE_COMPONENTS + 64], uz[256], un[MDG_MAX_ASSETS];
     const double *pn = 0, *pu = 0;
     if (io->normals) { for (int s = 0; s < e->P.n_normals; ++s) nz[s] = io->normals[s * N + i]; pn = nz; }
     if (io->uniforms) { for (int s = 0; s < e->P.n_uniforms; ++s) uz[s] = io->uniforms[s * N + i]; pu = uz; }
@@ -835,7 +972,7 @@ void orc_batch_reset(OrcBatch *b, const MdgStepIO *io, const MdgLaunch *L, const
     const int nA = e->P.n_assets, nN = e->P.n_normals, nU = e->P.n_uniforms;
     if (clear_nstep) e->ring_len = 0; /* offpolicy_q.py:94 */
     for (int t = 0; t < fill_ticks; ++t) {
-      double nz[64], uz[64];
+      double nz[16 * MDG_MAX_SINE_COMPONENTS + 64], uz[256];
       const double *pn = 0, *pu = 0;
       if (io->normals) { for (int s = 0; s < nN; ++s) nz[s] = io->normals[((int64_t)t * nN + s) * N + i]; pn = nz; }
       if (io->uniforms) { for (int s = 0; s < nU; ++s) uz[s] = io->uniforms[((int64_t)t * nU + s) * N + i]; pu = uz; }

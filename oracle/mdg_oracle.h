@@ -18,7 +18,8 @@
 extern "C" {
 #endif
 
-#define ORC_MAX_GSTATE (4 * MDG_MAX_ASSETS)
+#define ORC_MAX_GSTATE 320 /* 4 rows per trend asset; 4K(+1+T) per SINEDYNAMIC(TREND) asset */
+#define ORC_MAX_CTOR_U (3 * MDG_MAX_SINE_COMPONENTS)
 
 typedef struct OrcEnv {
   MdgParams P;
@@ -39,6 +40,10 @@ typedef struct OrcEnv {
   double A[MDG_MAX_ASSETS], B[MDG_MAX_ASSETS];
   double ring[MDG_MAX_NSTEP][MDG_MAX_ASSETS]; /* oldest first */
   int32_t ring_len;
+  /* test hook (single-asset SINEDYNAMIC* sources): canonical uniforms to use instead of the Philox
+   * constructor / reset() draws, slot 3c + {freq, mu, amp}; n_ctor_u = 0 -> Philox */
+  int32_t n_ctor_u;
+  double ctor_u[ORC_MAX_CTOR_U];
 } OrcEnv;
 
 typedef struct OrcStepOut {
@@ -62,6 +67,10 @@ double orc_draw_uniform(uint64_t seed, int64_t gid, int64_t tick, int slot);
 
 /* ---- single env ---- */
 void orc_init(OrcEnv *e, const MdgParams *P, const MdgReward *R, uint64_t seed, int64_t gid);
+/* as orc_init, with injected constructor uniforms (see OrcEnv.ctor_u) */
+void orc_init_inject(OrcEnv *e, const MdgParams *P, const MdgReward *R, uint64_t seed, int64_t gid,
+                     const double *ctor_u, int n_ctor_u);
+void orc_set_ctor_uniforms(OrcEnv *e, const double *u, int n);
 void orc_tick(OrcEnv *e, const double *normals, const double *uniforms);
 void orc_reset(OrcEnv *e, const double *normals, const double *uniforms, OrcStepOut *out);
 void orc_step(OrcEnv *e, int mode, const double *units, int asset_idx, const double *normals,

@@ -16,7 +16,8 @@ from madigan_b200 import _abi as A
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-ORC_MAX_GSTATE = 4 * A.MDG_MAX_ASSETS
+ORC_MAX_GSTATE = 320
+ORC_MAX_CTOR_U = 3 * A.MDG_MAX_SINE_COMPONENTS
 
 
 class OrcEnv(C.Structure):
@@ -27,7 +28,21 @@ class OrcEnv(C.Structure):
                 ("timestamp", C.c_int64), ("seed", C.c_uint64), ("gid", C.c_int64),
                 ("A", C.c_double * A.MDG_MAX_ASSETS), ("B", C.c_double * A.MDG_MAX_ASSETS),
                 ("ring", (C.c_double * A.MDG_MAX_ASSETS) * A.MDG_MAX_NSTEP),
-                ("ring_len", C.c_int32)]
+                ("ring_len", C.c_int32), ("n_ctor_u", C.c_int32), ("ctor_u", C.c_double * ORC_MAX_CTOR_U)]
+
+
+def host_params(params):
+    """The oracle reads MdgParams.gen_ext on the host: a copy of `params` whose gen_ext points at the numpy
+    table make_params attached (``ext_host``).  Returns (params, keepalive)."""
+    ext = getattr(params, "ext_host", None)
+    if ext is None:
+        return params, None
+    P = A.MdgParams.from_buffer_copy(params)
+    ext = np.ascontiguousarray(ext, dtype=np.float64)
+    P.gen_ext = ext.ctypes.data_as(C.c_void_p)
+    P.n_gen_ext = ext.size
+    P.ext_host = ext
+    return P, ext
 
 
 class OrcStepOut(C.Structure):
@@ -66,6 +81,11 @@ def lib():
             getattr(L, name).argtypes = [pe, C.POINTER(dbl)]
         L.orc_init.argtypes = [pe, C.POINTER(A.MdgParams), C.POINTER(A.MdgReward), C.c_uint64, C.c_int64]
         L.orc_init.restype = None
+        L.orc_init_inject.argtypes = [pe, C.POINTER(A.MdgParams), C.POINTER(A.MdgReward), C.c_uint64, C.c_int64,
+                                      C.c_void_p, C.c_int]
+        L.orc_init_inject.restype = None
+        L.orc_set_ctor_uniforms.argtypes = [pe, C.c_void_p, C.c_int]
+        L.orc_set_ctor_uniforms.restype = None
         L.orc_tick.argtypes = [pe, C.c_void_p, C.c_void_p]
         L.orc_tick.restype = None
         L.orc_reset.argtypes = [pe, C.c_void_p, C.c_void_p, C.POINTER(OrcStepOut)]
@@ -122,12 +142,14 @@ class OracleEnv:
     """One env: the reference's Env / Portfolio / Broker, restated.  Mirrors the members the
     reference's own tests touch (environments/cpp/tests/envTest.py)."""
 
-    def __init__(self, params, reward=None, seed=0, gid=0, construct=True):
+    def __init__(self, params, reward=None, seed=0, gid=0, construct=True, ctor_uniforms=None):
         self.L = lib()
         self.e = OrcEnv()
+        params, self._ext = host_params(params)
         self.P = params
-        self.L.orc_init(C.byref(self.e), C.byref(params), C.byref(reward) if reward is not None else None,
-                        seed, gid)
+        cu = None if ctor_uniforms is None else np.ascontiguousarray(ctor_uniforms, dtype=np.float64)
+        self.L.orc_init_inject(C.byref(self.e), C.byref(params), C.byref(reward) if reward is not None else None,
+                               seed, gid, _ptr(cu), 0 if cu is None else cu.size)
         self.nA = params.n_assets
         if construct:  # Env ctor consumes one tick (Env.h:160)
             self.tick()
@@ -153,6 +175,11 @@ class OracleEnv:
                     marginCall=bool(o.margin_call), agent_reward=np.array(o.agent_reward[:nA]),
                     shaped=np.array([list(o.shaped[k][:nA]) for k in range(o.n_popped)]).reshape(o.n_popped, nA),
                     n_popped=o.n_popped)
+
+    def set_ctor_uniforms(self, u):
+        """canonical uniforms the next reset() of a SINEDYNAMIC* source uses for (freq, mu, amp) per component"""
+        cu = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        self.L.orc_set_ctor_uniforms(C.byref(self.e), _ptr(cu), 0 if cu is None else cu.size)
 
     def reset(self, normals=None, uniforms=None):
         o = OrcStepOut()
@@ -261,6 +288,7 @@ class OracleBatch:
 
     def __init__(self, n_envs, params, reward=None, window=64, seed=0, env_offset=0, threads=1):
         self.L = lib()
+        params, self._ext = host_params(params)
         self.N, self.P, self.k = int(n_envs), params, int(window)
         self.R = reward if reward is not None else A.MdgReward(shaper=A.SHAPER_OFF, nstep=1)
         self.nA = params.n_assets

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libmadigan_ref.so")
 _LIB = None
 
 SYNTH, OU, OUPAIR, MULTIPAIR, SIMPLETREND, TRENDOU, TRENDYOU, SAWTOOTH, TRIANGLE, GAUSSIAN = range(10)
+SINEADDER, SINEDYNAMIC, SINEDYNAMICTREND = 10, 11, 12  # one asset; n_assets = number of components
 
 
 def available():
@@ -31,6 +32,9 @@ def lib():
         L.ref_env_next_draws.restype = C.c_int
         L.ref_env_next_draws.argtypes = [vp, dp, dp, C.c_int]
         L.ref_env_trend_state.argtypes = [vp, dp, ip, ip, ip]
+        L.ref_env_next_sine_draws.restype = C.c_int
+        L.ref_env_next_sine_draws.argtypes = [vp, dp, dp, dp, C.c_int]
+        L.ref_env_sine_state.argtypes = [vp, dp, dp, ip, ip, ip]
         L.ref_env_reset.argtypes = [vp, dp, dp, C.POINTER(C.c_longlong)]
         L.ref_env_step.argtypes = [vp, C.c_int, dp, C.c_int, dp, dp, C.POINTER(C.c_longlong), dp, ip, dp, dp, dp, ip, ip]
         L.ref_env_accounting.argtypes = [vp, dp, dp, dp]
@@ -50,7 +54,8 @@ class RefEnv:
     def __init__(self, kind, n_assets, params, init_cash=1_000_000., seed=12345):
         self.L = lib()
         p = np.ascontiguousarray(params, dtype=np.float64)
-        self.n = 2 if kind == OUPAIR else int(n_assets)
+        self.n = 2 if kind == OUPAIR else (1 if kind >= SINEADDER else int(n_assets))
+        self.ncomp = int(n_assets) if kind >= SINEADDER else 0
         self.h = self.L.ref_env_create(kind, int(n_assets), _dp(p), float(init_cash), int(seed))
 
     def __del__(self):
@@ -73,6 +78,22 @@ class RefEnv:
         n = self.L.ref_env_next_draws(self.h, _dp(z), _dp(u), int(after_reset))
         assert n == self.n
         return z, u
+
+    def next_sine_draws(self, after_reset=False):
+        """SineAdder / SineDynamic(Trend): (normals, uniforms, ctor_uniforms) of the next getData() -- after a reset()
+        first when after_reset -- in the oracle's slot order (see ref_driver.cpp)"""
+        z, u, cu = np.zeros(max(self.ncomp, 1)), np.ones(16), np.zeros(3 * self.ncomp)
+        n = self.L.ref_env_next_sine_draws(self.h, _dp(z), _dp(u), _dp(cu), int(after_reset))
+        assert n >= 1
+        return z[:n].copy(), u, cu
+
+    def sine_state(self, n_trends=0):
+        ip = C.POINTER(C.c_int)
+        comp, tc = np.zeros(4 * self.ncomp), np.zeros(1)
+        d, ln, tr = (np.zeros(max(n_trends, 1), dtype=np.int32) for _ in range(3))
+        self.L.ref_env_sine_state(self.h, _dp(comp), _dp(tc), d.ctypes.data_as(ip), ln.ctypes.data_as(ip), tr.ctypes.data_as(ip))
+        return dict(comp=comp, trend_component=tc[0], direction=d[:n_trends], length=ln[:n_trends],
+                    trending=tr[:n_trends].astype(bool))
 
     def trend_state(self):
         ip = C.POINTER(C.c_int)

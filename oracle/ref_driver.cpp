@@ -109,6 +109,11 @@ struct RefEnv {
   Gaussian* gauss = nullptr;
   MultiPair* multi = nullptr;
   std::vector<std::default_random_engine> clones;  // kind 3: one engine per pair
+  // kinds 10-12: SineAdder, SineDynamic, SineDynamicTrend (one asset, ncomp components)
+  SineAdder* sadd = nullptr;
+  SineDynamic* sdyn = nullptr;
+  SineDynamicTrend* sdt = nullptr;
+  int ncomp = 0, ntrend = 0;
 };
 
 }  // namespace
@@ -141,6 +146,56 @@ void* ref_env_create(int kind, int n_assets, const double* p, double init_cash, 
     r->gauss = s.get();
     r->cn.assign(n_assets, std::normal_distribution<double>(0., 1.));
     src = std::move(s);
+  } else if (kind == 10) {  // SineAdder: p = freq,mu,amp,phase per component then dX, noise; n_assets = components
+    const int K = n_assets;
+    std::vector<double> f(K), mu(K), amp(K), ph(K);
+    for (int i = 0; i < K; ++i) { f[i] = p[4 * i]; mu[i] = p[4 * i + 1]; amp[i] = p[4 * i + 2]; ph[i] = p[4 * i + 3]; }
+    auto s = std::make_unique<SineAdder>(f, mu, amp, ph, p[4 * K], p[4 * K + 1]);
+    s->generator.seed(seed);
+    s->noiseDistribution.reset();
+    s->timestamp_ = 0;  // left uninitialised by the reference (DataSource.h:284)
+    r->sadd = s.get();
+    r->ncomp = K;
+    n_assets = 1;
+    src = std::move(s);
+  } else if (kind == 11 || kind == 12) {
+    // p = (freq lo,hi,step, mu lo,hi,step, amp lo,hi,step) per component, dX, noise[, T, (lenLo,lenHi,incr,prob) per trend]
+    const int K = n_assets;
+    std::vector<std::array<double, 3>> fr(K), mr(K), ar(K);
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < 3; ++j) { fr[i][j] = p[9 * i + j]; mr[i][j] = p[9 * i + 3 + j]; ar[i][j] = p[9 * i + 6 + j]; }
+    const double dX = p[9 * K], noise = p[9 * K + 1];
+    if (kind == 11) {
+      auto s = std::make_unique<SineDynamic>(fr, mr, ar, dX, noise);
+      s->generator.seed(seed);
+      s->noiseDistribution.reset();
+      s->timestamp_ = 0;
+      s->boolDist.generator.state[0] = 0x9E3779B97F4A7C15ull ^ seed;  // std::random_device in the reference
+      s->boolDist.generator.state[1] = 0xD1B54A32D192ED03ull + seed;
+      s->boolDist.counter = 0;
+      r->sdyn = s.get();
+      src = std::move(s);
+    } else {
+      const int T = (int)p[9 * K + 2];
+      std::vector<std::array<int, 2>> tr(T);
+      std::vector<double> incr(T), prob(T);
+      for (int j = 0; j < T; ++j) {
+        const double* q = p + 9 * K + 3 + 4 * j;
+        tr[j] = {(int)q[0], (int)q[1]}; incr[j] = q[2]; prob[j] = q[3];
+      }
+      auto s = std::make_unique<SineDynamicTrend>(fr, mr, ar, tr, incr, prob, dX, noise);
+      s->generator.seed(seed);
+      s->noiseDistribution.reset();
+      s->timestamp_ = 0;
+      s->boolDist.generator.state[0] = 0x9E3779B97F4A7C15ull ^ seed;
+      s->boolDist.generator.state[1] = 0xD1B54A32D192ED03ull + seed;
+      s->boolDist.counter = 0;
+      r->sdt = s.get();
+      r->ntrend = T;
+      src = std::move(s);
+    }
+    r->ncomp = K;
+    n_assets = 1;
   } else if (kind == 1) {
     std::vector<double> m(n_assets), th(n_assets), ph(n_assets);
     for (int i = 0; i < n_assets; ++i) { m[i] = p[3 * i]; th[i] = p[3 * i + 1]; ph[i] = p[3 * i + 2]; }
@@ -200,7 +255,7 @@ void* ref_env_create(int kind, int n_assets, const double* p, double init_cash, 
   r->n_assets = n_assets;
   // Env's own constructor builds a source with the right number of assets (and ticks it once); it is then
   // replaced by the re-seedable one, as Env::setDataSource is meant to be used (Env.h:33-34,167-172)
-  if (kind == 3 || (kind >= 4 && kind <= 6) || kind == 9) {
+  if (kind == 3 || (kind >= 4 && kind <= 6) || kind >= 9) {
     std::vector<double> ones((size_t)n_assets, 1.);
     Config inner{{"mean", ones}, {"theta", ones}, {"phi", ones}};
     Config cfg{{"data_source_config", inner}};
@@ -317,6 +372,70 @@ int ref_env_next_draws(void* h, double* z, double* u, int after_reset) {
     return -1;
   }
   return n;
+}
+
+// SineAdder / SineDynamic / SineDynamicTrend: the draws of the next getData() (after a reset() first when
+// after_reset), taken from COPIES of the live engine, distributions and boolean generator:
+//   z      SineAdder: one standard normal per component; SineDynamic*: one standard normal
+//   u      SineDynamic*: u[0] packs the random booleans (boolean b = bit 52-b of u 2^53; 3 per component in the
+//          order mu, amp, freq, then bit 3K+j = direction of trend j), u[1+2j] the trend-start test of trend j,
+//          u[2+2j] the u whose oracle mapping is the drawn trend length; unused ones 1.0
+//   ctor_u the 3K canonical uniforms reset() turns into (freq, mu, amp) per component (after_reset only)
+int ref_env_next_sine_draws(void* h, double* z, double* u, double* ctor_u, int after_reset) {
+  auto* r = (RefEnv*)h;
+  using NP = std::normal_distribution<double>::param_type;
+  std::uniform_real_distribution<double> U(0., 1.);
+  const int K = r->ncomp;
+  if (r->sadd) {
+    auto g = r->sadd->generator;
+    auto nd = r->sadd->noiseDistribution;
+    for (int i = 0; i < K; ++i) z[i] = nd(g, NP(0., 1.));
+    return K;
+  }
+  if (!r->sdyn && !r->sdt) return -1;
+  auto g = r->sdyn ? r->sdyn->generator : r->sdt->generator;
+  auto nd = r->sdyn ? r->sdyn->noiseDistribution : r->sdt->noiseDistribution;
+  auto b = r->sdyn ? r->sdyn->boolDist : r->sdt->boolDist;
+  if (after_reset)
+    for (int i = 0; i < 3 * K; ++i) ctor_u[i] = U(g);  // freqDist, muDist, ampDist per component, :783-787
+  unsigned long long bits = 0;
+  for (int i = 0; i < 3 * K; ++i)
+    if (b.randBool()) bits |= 1ull << (52 - i);
+  const int T = r->ntrend;
+  for (int j = 0; j < 1 + 2 * T; ++j) u[j] = 1.;
+  if (r->sdt) {
+    SineDynamicTrend& s = *r->sdt;
+    for (int j = 0; j < T; ++j) {
+      if (s.trending[j]) continue;
+      const double rnd = U(g);
+      u[1 + 2 * j] = rnd;
+      if (rnd < s.trendProb[j]) {
+        if (b.randBool()) bits |= 1ull << (52 - (3 * K + j));
+        auto ld = s.trendLenDist[j];
+        const int L = ld(g);
+        u[2 + 2 * j] = ((double)(L - ld.a()) + 0.5) / (double)(ld.b() - ld.a() + 1);
+      }
+    }
+  }
+  u[0] = (double)bits * 0x1.0p-53;
+  z[0] = nd(g, NP(0., 1.));
+  return 1;
+}
+
+// SineDynamic*: freq, mu, amp, oscillator phase per component [4K], then trendComponent and per trend
+// (direction, remaining length, trending) for SineDynamicTrend
+void ref_env_sine_state(void* h, double* comp, double* trend_component, int* dir, int* len, int* trending) {
+  auto* r = (RefEnv*)h;
+  const int K = r->ncomp;
+  for (int i = 0; i < K; ++i) {
+    if (r->sdyn) { comp[4 * i] = r->sdyn->freq[i]; comp[4 * i + 1] = r->sdyn->mu[i]; comp[4 * i + 2] = r->sdyn->amp[i]; comp[4 * i + 3] = r->sdyn->oscillators[i].phasor; }
+    if (r->sdt) { comp[4 * i] = r->sdt->freq[i]; comp[4 * i + 1] = r->sdt->mu[i]; comp[4 * i + 2] = r->sdt->amp[i]; comp[4 * i + 3] = r->sdt->oscillators[i].phasor; }
+    if (r->sadd) comp[i] = r->sadd->x[i];
+  }
+  if (r->sdt) {
+    *trend_component = r->sdt->trendComponent;
+    for (int j = 0; j < r->ntrend; ++j) { dir[j] = r->sdt->currentDirection[j]; len[j] = r->sdt->currentTrendLen[j]; trending[j] = r->sdt->trending[j]; }
+  }
 }
 
 // generator internals of the trend sources for state comparison: dY, direction, remaining length, trending

@@ -42,8 +42,28 @@ COMPOSITE16 = {
 PAIRS8 = {f"pair{i}": {"data_source_type": "OUPair",
                        "data_source_config": {"theta": .015, "phi": .01, "noise": .03}} for i in range(8)}
 
+SINE_DYN = {"freqRange": [[.1, 1., .01], [0.3, 3.0, .01], [5., 15., .1], [10., 50., .1]],
+            "muRange": [[1., 5., .02], [.3, 3., .05], [.2, 5., .02], [.5, 5., .02]],
+            "ampRange": [[1., 5., .01], [.3, 3., .02], [.2, 2., .04], [.5, 5., .05]], "dX": 0.01, "noise": .3}
+SINE_TREND = dict(SINE_DYN, trendRange=[[5, 40], [10, 30]], trendIncr=[0.01, 0.02], trendProb=[.02, .05])
+SINE_ADDER = {"freq": [1., 0.3, 2., 0.5], "mu": [2., 2.1, 2.2, 2.3], "amp": [1., 1.2, 1.3, 1.],
+              "phase": [0., 1., 2., 1.], "dX": 0.01, "noise": .05}
+SINE_MIX = {
+    "dyn": {"data_source_type": "SineDynamic", "data_source_config": SINE_DYN},
+    "pair": {"data_source_type": "OUPair", "data_source_config": {"theta": .015, "phi": .01, "noise": .03}},
+    "dyntrend": {"data_source_type": "SineDynamicTrend", "data_source_config": SINE_TREND},
+    "trendou": COMPOSITE16["trendou"],
+    "dyn2": {"data_source_type": "SineDynamic", "data_source_config": dict(
+        freqRange=[[.5, 2., .05], [1., 20., .5], [2., 4., .01]], muRange=[[1., 2., .1]] * 3,
+        ampRange=[[.1, .5, .05]] * 3, dX=0.02, noise=0.)},
+}
+
 CASES = {
     # name: (data_source_type, data_source_config, has_transcendental_prices)
+    "sineadder": ("SineAdder", SINE_ADDER, True),
+    "sinedynamic": ("SineDynamic", SINE_DYN, False),       # wave tables come from the host: arithmetic only
+    "sinedyntrend": ("SineDynamicTrend", SINE_TREND, False),
+    "sine_mix": ("Composite", SINE_MIX, False),
     "synth4": ("Synth", None, True),
     "ou1": ("OU", {"mean": [10.], "theta": [.08], "phi": [.04]}, False),
     "ou3": ("OU", {"mean": [10., 5., 1.], "theta": [.08, .15, .15], "phi": [.04, .02, .01]}, False),
@@ -310,6 +330,39 @@ def test_free_running_philox_matches_oracle():
         orc.step(units)
         close(cpu(env.t["price"]), orc.state()["price"], rtol=1e-9)
         assert np.array_equal(cpu(env.t["ledger"]), orc.state()["ledger"])
+
+
+@pytest.mark.parametrize("case", ["sinedynamic", "sine_mix", "sineadder"])
+def test_free_running_sine_sources_match_oracle(case):
+    """Free-running Philox with the SINE* sources: the constructor and reset() draws of (freq, mu, amp) (streams 3
+    and 2), the packed random booleans and the trend draws are bit-identical on both sides; normals go through CUDA's
+    log/sincos -> 1e-9 on prices.  Auto-reset on, so the list-driven refill kernel runs these generators too."""
+    N = 300
+    env, orc, P = make_pair(case, N, window=8, margins=(.1, .25), costs=(.02, 0., .001, 0.), seed=77, env_offset=500)
+    orc.reset(fill_ticks=1, clear_nstep=False)
+    rng = np.random.default_rng(5)
+    nA = P.n_assets
+    exact_rows = []  # generator-state rows that no normal draw touches: freq, mu, amp, phasor, flags
+    for i in range(nA):
+        g = P.gen[i]
+        if g.type in (10, 11):
+            exact_rows += list(range(g.gslot, g.gslot + 4 * int(g.p[0])))
+    n_done = 0
+    for t in range(40):
+        units = gen_units(rng, orc, N, nA, 300_000.)
+        env.step(torch.from_numpy(units), auto_reset=True)
+        orc.step(units)
+        done = orc.done.astype(bool)
+        assert np.array_equal(cpu(env.t["done"]), orc.done)
+        n_done += int(done.sum())
+        if done.any():  # the CUDA side has already refilled these envs (auto_reset)
+            orc.reset(mask=orc.done.copy(), fill_ticks=8)
+        st = orc.state()
+        assert np.array_equal(cpu(env.t["ledger"]), st["ledger"])
+        if exact_rows:
+            assert same_bits(cpu(env.t["gstate"])[exact_rows], st["gstate"][exact_rows]), f"step {t} gstate"
+        close(cpu(env.t["price"]), st["price"], rtol=1e-9)
+    assert n_done > 0 or case == "sineadder"
 
 
 def test_sharding_is_invisible():

@@ -215,3 +215,108 @@ def test_reference_timestamp_counts_ticks():
     t1 = r.step()["timestamp"]
     t2 = r.step(np.zeros(2))["timestamp"]
     assert t1 - t0 == 1 and t2 - t1 == 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SineAdder / SineDynamic / SineDynamicTrend (DataSource.cpp:663-673, 802-841, 1002-1047; WaveTableOsc.h;
+# randomBoolGenerator.h) -- left unpinned by the reference's own tests
+# ---------------------------------------------------------------------------------------------------------
+SINE_DYN = dict(freqRange=[[.1, 1., .01], [0.3, 3.0, .01], [5., 15., .1], [10., 50., .1]],
+                muRange=[[1., 5., .02], [.3, 3., .05], [.2, 5., .02], [.5, 5., .02]],
+                ampRange=[[1., 5., .01], [.3, 3., .02], [.2, 2., .04], [.5, 5., .05]], dX=0.01, noise=.3)
+SINE_CASES = {
+    "adder": (ref.SINEADDER, "SineAdder", dict(freq=[1., 0.3, 2., 0.5], mu=[2., 2.1, 2.2, 2.3], amp=[1., 1.2, 1.3, 1.],
+                                                phase=[0., 1., 2., 1.], dX=0.01, noise=.05)),
+    "dynamic": (ref.SINEDYNAMIC, "SineDynamic", SINE_DYN),
+    "dynamic_3comp": (ref.SINEDYNAMIC, "SineDynamic",
+                      dict(freqRange=[[.5, 2., .05], [1., 20., .5], [2., 4., .01]], muRange=[[1., 2., .1]] * 3,
+                           ampRange=[[.1, .5, .05]] * 3, dX=0.02, noise=0.)),
+    # short, likely trends so that the state machine turns over many times in a few thousand ticks
+    "trend": (ref.SINEDYNAMICTREND, "SineDynamicTrend",
+              dict(SINE_DYN, trendRange=[[5, 40], [10, 30]], trendIncr=[0.01, 0.02], trendProb=[.02, .05])),
+    "trend_default_shape": (ref.SINEDYNAMICTREND, "SineDynamicTrend",
+                            dict(SINE_DYN, trendRange=[[100, 500], [100, 300]], trendIncr=[0.1, 0.2],
+                                 trendProb=[.001, .01], noise=1.)),
+}
+
+
+def build_sine(case, seed):
+    kind, ds_type, cfg = SINE_CASES[case]
+    if kind == ref.SINEADDER:
+        K = len(cfg["freq"])
+        p = [x for i in range(K) for x in (cfg["freq"][i], cfg["mu"][i], cfg["amp"][i], cfg["phase"][i])]
+        p += [cfg["dX"], cfg["noise"]]
+    else:
+        K = len(cfg["freqRange"])
+        p = [x for i in range(K) for x in cfg["freqRange"][i] + cfg["muRange"][i] + cfg["ampRange"][i]]
+        p += [cfg["dX"], cfg["noise"]]
+        if kind == ref.SINEDYNAMICTREND:
+            T = len(cfg["trendProb"])
+            p += [T] + [x for j in range(T) for x in (*cfg["trendRange"][j], cfg["trendIncr"][j], cfg["trendProb"][j])]
+    r = ref.RefEnv(kind, K, p, seed=seed)
+    r.set(.1, .25, .02, 0., .001, 0.)
+    P, names = make_params(ds_type, cfg, required_margin=.1, maintenance_margin=.25, transaction_cost_rel=.02,
+                           slippage_rel=.001)
+    assert P.n_assets == 1 and P.gen[0].nslot == 0
+    return r, OracleEnv(P, construct=False), kind, K
+
+
+def oracle_sine_state(o, kind, K, T):
+    gs = np.ctypeslib.as_array(o.e.gstate)
+    if kind == ref.SINEADDER:
+        return dict(comp=gs[:K].copy())
+    out = dict(comp=gs[:4 * K].copy())
+    if kind == ref.SINEDYNAMICTREND:
+        f = gs[4 * K + 1: 4 * K + 1 + T].copy().view(np.int64)
+        out.update(trend_component=gs[4 * K], direction=np.where(f & 2, 1, -1), length=(f >> 32).astype(np.int32),
+                   trending=(f & 1) == 1)
+    return out
+
+
+@pytest.mark.parametrize("case", list(SINE_CASES))
+@pytest.mark.parametrize("seed", [11, 909])
+def test_sine_sources_bit_exact_vs_reference(case, seed):
+    """SineAdder, SineDynamic, SineDynamicTrend through Env.step: prices, the bounded parameter walks, the
+    wave-table oscillator phase, the trend state machine and reset()'s re-sampled (freq, mu, amp), bit for bit."""
+    rng = np.random.default_rng(seed)
+    r, o, kind, K = build_sine(case, seed)
+    T = len(SINE_CASES[case][2].get("trendProb", []))
+
+    def do_reset():
+        z, u, cu = r.next_sine_draws(after_reset=True)
+        o.set_ctor_uniforms(cu if kind != ref.SINEADDER else None)
+        rs, os_ = r.reset(), o.reset(normals=z, uniforms=u)
+        assert same(rs["price"], os_["price"]), (rs["price"], os_["price"])
+
+    def compare_state(t):
+        a = r.sine_state(T)
+        b = oracle_sine_state(o, kind, K, T)
+        na = K if kind == ref.SINEADDER else 4 * K
+        assert same(a["comp"][:na], b["comp"]), f"step {t}: {a['comp'][:na]} vs {b['comp']}"
+        if kind == ref.SINEDYNAMICTREND:
+            assert same(a["trend_component"], b["trend_component"]), f"step {t}"
+            assert np.array_equal(a["trending"], b["trending"]), f"step {t}"
+            live = a["trending"]
+            assert np.array_equal(a["length"][live], b["length"][live]), f"step {t}"
+            assert np.array_equal(a["direction"][live], b["direction"][live]), f"step {t}"
+            return int(live.sum())
+        return 0
+
+    do_reset()
+    compare_state(-1)
+    n_trending, resets = 0, 0
+    for t in range(3000):
+        z, u, _ = r.next_sine_draws()
+        units = gen_units(rng, o, 1, 20_000.) if t % 5 else None
+        ro, oo = r.step(units), o.step(units, normals=z, uniforms=u)
+        assert same(ro["price"], oo["price"]), f"step {t}: {ro['price']} vs {oo['price']}"
+        assert same(ro["portfolio"], oo["portfolio"]) and same(ro["reward"], oo["reward"]), f"step {t}"
+        assert ro["done"] == oo["done"]
+        n_trending += compare_state(t)
+        if oo["done"] or t % 700 == 699:
+            resets += 1
+            do_reset()
+            compare_state(t)
+    assert resets >= 4
+    if case == "trend":
+        assert n_trending > 300
