@@ -158,6 +158,9 @@ struct ResetWsArgs {
   int chunk;    // ticks per shared-memory chunk
   int n_groups;
   int8_t leader[MDG_MAX_ASSETS];
+  // refill kernel: generator group run by each thread (-1: none).  Groups of one generator type share a warp,
+  // different types go to different warps, so that a Composite's 64-tick recurrences do not serialise by type.
+  int8_t group_of_thread[128];
 };
 
 __global__ void __launch_bounds__(256) reset_scan_kernel(const __grid_constant__ ResetWsArgs a) {
@@ -207,8 +210,9 @@ __global__ void __launch_bounds__(kFillBlock) reset_fill_kernel(const __grid_con
       a.IO.obs_port[((int64_t)a.L.head * (na + 1)) * N + e] = (cash - 0.) / eq;  // newest row = current state
     }
     // generator state of group `tid` (warp 0, lanes < nlead) in registers for the whole fast-forward
-    const bool worker = tid < nlead;
-    const int i0 = worker ? a.leader[tid] : 0;
+    const int grp = a.group_of_thread[tid];
+    const bool worker = grp >= 0 && grp < nlead;
+    const int i0 = worker ? a.leader[grp] : 0;
     const MdgAssetGen& g0 = P.gen[i0];
     const bool is_pair = g0.type == MDG_GEN_OUPAIR;
     const int cnt = is_pair ? 2 : 1;
@@ -490,6 +494,17 @@ static int fill_ws_args(ResetWsArgs& a, const MdgParams* P, const MdgState* S, c
     a.chunk = a.chunk < cap ? a.chunk : (cap > 0 ? cap : 1);
   }
   a.n_groups = fill_groups(*P, a.leader);
+  static_assert(kFillBlock == 128, "group_of_thread is sized for 128 threads");
+  for (int t = 0; t < kFillBlock; ++t) a.group_of_thread[t] = -1;
+  int types[MDG_MAX_ASSETS], n_types = 0, used[kFillBlock / 32] = {0, 0, 0, 0};
+  for (int g = 0; g < a.n_groups; ++g) {
+    const int ty = P->gen[a.leader[g]].type;
+    int k = 0;
+    while (k < n_types && types[k] != ty) ++k;
+    if (k == n_types) types[n_types++] = ty;
+    const int w = k % (kFillBlock / 32);
+    a.group_of_thread[32 * w + used[w]++] = (int8_t)g;  // at most MDG_MAX_ASSETS groups: a warp never overflows
+  }
   return MDG_OK;
 }
 static int launch_fill(const ResetWsArgs& a, int64_t max_listed) {
@@ -577,6 +592,13 @@ extern "C" int mdg_refresh_folds(const MdgParams* P, const MdgState* S, const Md
   refresh_folds_kernel<<<grid, 128, 0, (cudaStream_t)L->stream>>>(a);
   return cuda_err(cudaGetLastError(), "mdg_refresh_folds launch");
 }
+
+#ifdef MDG_PHASE_CLOCKS
+// profiling builds only: copies the 64 x 64 phase clocks of the last step launch to the host
+extern "C" int mdg_debug_phase_clocks(long long* out) {
+  return cuda_err(cudaMemcpyFromSymbol(out, mdg::g_phase_clk, sizeof(long long) * 64 * 64), "phase clocks");
+}
+#endif
 
 extern "C" int mdg_abi_version(void) { return MDG_ABI_VERSION; }
 extern "C" const char* mdg_last_error(void) { return err_buf(); }

@@ -151,9 +151,12 @@ class Env:
         N, nA, k, dev = self.N, self.nA, self.k, self.device
         f8 = dict(dtype=torch.float64, device=dev)
         z = torch.zeros
+        # price, ledger, mean_entry, borrowed are equally spaced views of ONE slab: the step kernel then fetches a
+        # pair's eight state rows with a single 3-D TMA tensor copy (csrc/mdg_step_kernel.cuh, tm_state)
+        slab = z((4, nA, N), **f8)
         self.t = dict(
-            price=z((nA, N), **f8), ledger=z((nA, N), **f8), mean_entry=z((nA, N), **f8),
-            borrowed=z((nA, N), **f8), cash=z((N,), **f8), gstate=z((max(1, self.P.n_gstate), N), **f8),
+            price=slab[0], ledger=slab[1], mean_entry=slab[2],
+            borrowed=slab[3], cash=z((N,), **f8), gstate=z((max(1, self.P.n_gstate), N), **f8),
             timestamp=z((N,), dtype=torch.int64, device=dev), folds=z((5, N), **f8),
             reset_ts=z((N,), dtype=torch.int64, device=dev),
             shaper_A=z((self.ra, N), **f8), shaper_B=z((self.ra, N), **f8),

@@ -20,4 +20,9 @@ for i in range(K):
     env._reset_launch(env.t["done"], 64, True, None, None); ev[i][2].record()
 torch.cuda.synchronize()
 st = sorted(a.elapsed_time(b) for a, b, _ in ev); rs = sorted(b.elapsed_time(c) for _, b, c in ev)
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for i in range(K): env.step(acts[i % 4], auto_reset=True)
+b.record(); torch.cuda.synchronize()
+print(f"C4 fused step+refill {a.elapsed_time(b) / K * 1e3:.1f} us per step")
 print(f"C4 step kernel median {st[K//2]*1e3:.1f} us, masked reset {rs[K//2]*1e3:.1f} us, done rate {float(env.t['done'].float().mean()):.4f}")

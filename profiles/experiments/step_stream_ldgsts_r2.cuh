@@ -10,7 +10,6 @@
 //   reward, done -> newest observation-ring row -> agent reward -> shaped reward.
 // HBM-bound integer/fp64 work: no tensor cores.
 #pragma once
-#include <cuda.h>
 #include <math.h>
 #include <stdio.h>
 
@@ -32,11 +31,6 @@ struct StepArgs {
   int bulk;  // set by launch_step: the pairs' state rows reach the block through cp.async.bulk + mbarrier (see step_body)
   int* done_count;  // nullable (auto-reset): number of envs that finished this step ...
   int* done_list;   // ... and their indices, appended warp by warp in the kernel's tail
-  // bulk == 2: tensor maps of the state slab (N x nA x {price, ledger, mean entry, borrowed}) and of the caller's units
-  // matrix (nA x N), filled by launch_step; tma_units: the units come through the ring too
-  int tma_units;
-  alignas(64) CUtensorMap tm_state;
-  alignas(64) CUtensorMap tm_units;
 };
 
 constexpr int kBlock = 128;
@@ -63,7 +57,6 @@ constexpr int kBlock = 128;
 constexpr int kRngUnroll = MDG_RNG_UNROLL, kTailUnroll = MDG_TAIL_UNROLL;  // #pragma unroll does not expand macros
 
 // ---- bulk-copy staging of the state rows (sm_90+: cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS)
-constexpr int kStageDoubles = 11 * 128;  // per stage and 128-thread block: nine rows + the pair's units (2 per env)
 constexpr int kBulkRows = 9;    // per pair: price x2, ledger x2, mean entry x2, borrowed margin x2, the pair's mean
 constexpr int kBulkStages = 2;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -524,16 +517,13 @@ __device__ __forceinline__ int gen_state_rows(const MdgAssetGen& g) {
 //     wave (that launch is latency-bound: a second wave would cost as much as the first);
 //   168 registers -> 3 blocks per SM, no spills: best throughput when there are many waves (>= 262,144 envs).
 // (64-thread blocks x 7 per SM at 144 registers were measured slower than either.)
-// -DMDG_PHASE_CLOCKS (profiling builds only, profiles/phase_clocks.py): thread MDG_PCLK_TID of the first 64 blocks
-// records clock64() at the phase boundaries of its step
+// -DMDG_PHASE_CLOCKS (profiling builds only, profiles/phase_clocks.py): thread 0 of the first 64 blocks records
+// clock64() at the phase boundaries of its step
 #ifdef MDG_PHASE_CLOCKS
-#ifndef MDG_PCLK_TID
-#define MDG_PCLK_TID 0
-#endif
 __device__ long long g_phase_clk[64 * 64];
-#define MDG_PCLK(slot)                                                                                     \
-  do {                                                                                                     \
-    if (threadIdx.x == MDG_PCLK_TID && blockIdx.x < 64) g_phase_clk[blockIdx.x * 64 + (slot)] = clock64(); \
+#define MDG_PCLK(slot)                                                                          \
+  do {                                                                                          \
+    if (threadIdx.x == 0 && blockIdx.x < 64) g_phase_clk[blockIdx.x * 64 + (slot)] = clock64(); \
   } while (0)
 #else
 #define MDG_PCLK(slot)
@@ -544,7 +534,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   MDG_PCLK(0);
   // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff (and, in the
   // all-pairs kernel, this step's normals before they are consumed; see stash_normal_row)
-  extern __shared__ __align__(128) double stash[];
+  extern __shared__ double stash[];
   const MdgParams& P = a.P;
   const MdgState& S = a.S;
   const int64_t N = a.L.n_envs;
@@ -557,61 +547,45 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   // vectors (one per pair) that bypass L1, so that the 64 KB of unit lines per SM do not evict the prefetched state
   const bool units_v2 = MDG_UNITS_CG && PAIRS && mode == MDG_MODE_MULTI && a.units_v2;
   if (e >= N) return;
-  // Bulk staging (all-pairs kernel, whole blocks only): the nine 1-KB state rows a block needs for a pair are
-  // contiguous in the [rows][N] tensors, so one elected thread fetches them with nine cp.async.bulk copies into a
-  // two-stage shared-memory ring, two pairs ahead, completion on an mbarrier per stage.  The bytes are in flight
-  // without holding registers (the register prefetch of round 1 spilled at the 128-register budget) and arrive in
-  // shared memory instead of L2 (the prefetch.global.L1 hints still left an L2 round trip on every first use).
+  // Asynchronous staging of the pairs' state (all-pairs kernel, one-wave variant): every thread copies ITS OWN nine
+  // values of a pair (price, ledger, mean entry, borrowed x2, the pair's mean) from the [rows][N] tensors into its
+  // column of a two-stage shared-memory ring with cp.async (LDGSTS), two pairs ahead.  The bytes are in flight
+  // without holding registers (the register prefetch of round 1 spilled at the 128-register budget), nothing is
+  // shared between threads, so there is no barrier and no waiting for another warp, and a copy costs one issue
+  // slot.  Measured alternatives (profiles/r2_notes.md section 1b): cp.async.bulk + mbarrier per block (a
+  // __syncthreads per pair: every warp waits for the slowest, ~1,000 of a pair's ~4,700 cycles) and per warp (no
+  // waiting, but ~1,100 cycles per pair to issue the 9 bulk copies + expect_tx).
   constexpr bool bulk = PAIRS && BULK;
   double* ring = stash + 2 * na * BS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kBulkStages * kStageDoubles);
-  const int64_t e0 = (int64_t)blockIdx.x * BS;
-  const bool tma = bulk && a.bulk == 2;
-  const bool tma_units = tma && a.tma_units;
-  // bulk == 2: ONE 3-D tensor copy brings the pair's eight state rows (box 128 envs x 2 assets x 4 tensors), one
-  // 2-D tensor copy gathers the pair's 16 bytes of every env's units row (box 2 x 128), one bulk copy the mean row
-  auto tma_issue = [&](int pp, int stage) {  // one thread
-    const uint32_t mb = smem_u32(&full[stage]);
-    double* sb = ring + stage * kStageDoubles;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb),
-                 "r"((uint32_t)((kBulkRows + (tma_units ? 2 : 0)) * BS * sizeof(double)))
-                 : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            smem_u32(sb)),
-        "l"(&a.tm_state), "r"((int)e0), "r"(2 * pp), "r"(0), "r"(mb)
-        : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(sb + 8 * BS)),
-                 "l"(S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e0), "r"((uint32_t)(BS * sizeof(double))), "r"(mb)
-                 : "memory");
-    if (tma_units)
-      asm volatile(
-          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-              smem_u32(sb + kBulkRows * BS)),
-          "l"(&a.tm_units), "r"(2 * pp), "r"((int)e0), "r"(mb)
-          : "memory");
-  };
-  auto bulk_issue = [&](int pp, int stage) {  // one thread
-    if (tma) { tma_issue(pp, stage); return; }
-    const uint32_t mb = smem_u32(&full[stage]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb),
-                 "r"((uint32_t)(kBulkRows * BS * sizeof(double)))
-                 : "memory");
-    const int64_t o0 = (int64_t)(2 * pp) * N + e0, o1 = o0 + N;
+  auto stage_issue = [&](int pp, int stage) {
+    const uint32_t dst = smem_u32(ring + stage * kBulkRows * BS + tid);
+    const int64_t o0 = (int64_t)(2 * pp) * N + e, o1 = o0 + N;
     const double* src[kBulkRows] = {S.price + o0, S.price + o1, S.ledger + o0, S.ledger + o1, S.mean_entry + o0,
                                     S.mean_entry + o1, S.borrowed + o0, S.borrowed + o1,
-                                    S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e0};
+                                    S.gstate + (int64_t)P.gen[2 * pp].gslot * N + e};
 #pragma unroll
     for (int r = 0; r < kBulkRows; ++r)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_u32(ring + stage * kStageDoubles + r * BS)),
-                   "l"(src[r]), "r"((uint32_t)(BS * sizeof(double))), "r"(mb)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)(r * BS * sizeof(double))), "l"(src[r])
                    : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  if (bulk) {
+    stage_issue(0, 0);
+    if (na > 2) stage_issue(1, 1);
+  }
   const bool shaping = (a.R.shaper != MDG_SHAPER_OFF) && (mode != MDG_MODE_HOLD);
   const double* urow = a.IO.units ? a.IO.units + (mode == MDG_MODE_MULTI ? e * na : e) : nullptr;  // unused with actions
   const bool moments = shaping && (a.R.shaper == MDG_SHAPER_DSR || a.R.shaper == MDG_SHAPER_DDR);
+  // The thread's units row (one 128-byte line, four DRAM sectors) is consumed 16 bytes per pair: without help every
+  // second pair waits a full DRAM round trip at the top of its transaction (profiles/phase_clocks.py: ~1,700 of the
+  // ~4,700 cycles of a pair).  All four sectors are requested into L2 here, and the loop keeps the next pair's
+  // 16 bytes in flight in registers.
+  double2 u_next = make_double2(0., 0.);
+  if (units_v2) {
+#pragma unroll
+    for (int sct = 1; sct < 4; ++sct) asm volatile("prefetch.global.L2 [%0];" ::"l"(urow + 4 * sct));
+    u_next = __ldcg(reinterpret_cast<const double2*>(urow));
+  }
   auto prefetch_hint = [&](int pp) {
     const int64_t o0 = (int64_t)(2 * pp) * N + e, o1 = o0 + N;
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.price + o0));
@@ -657,19 +631,6 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   A.rBM = S.folds[(int64_t)MDG_FOLD_BM * N + e];
   A.rSE = S.folds[(int64_t)MDG_FOLD_SE * N + e];
   A.G = S.folds[(int64_t)MDG_FOLD_G * N + e];
-  // The ring is set up AFTER the loads above have been issued: the first copy instructions of a kernel keep their
-  // thread busy for ~4,000 cycles (profiles/phase_clocks.py: the issuing warp left the prologue 4,000 cycles after
-  // the others, and they waited for it at the first pair), which now overlaps the latency of these loads.  Only the
-  // first pair's rows are requested here, the second pair's after the normals.
-  if (bulk) {
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) bulk_issue(0, 0);
-  }
   A.pav = A.pml = A.pbm = A.pse = A.nav = A.gsum = 0.;
   A.bad_risk = false;
   const double prevEq = A.cash + A.rAV - A.rBM;  // Env.h:190,208,234
@@ -715,7 +676,6 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
         if (2 * b + 1 < nslots) st[stash_normal_row(2 * b + 1) * BS] = zb;
       }
     }
-    if (bulk && tid == 0 && na > 2) bulk_issue(1, 1);
     MDG_PCLK(2);
 #pragma unroll 1
     for (int p = 0; p < np; ++p) {
@@ -725,21 +685,13 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
       double mean;
       if (bulk) {
         const int stage = p & 1;
-        mbar_wait(&full[stage], (uint32_t)((p >> 1) & 1));
-        if (p == 0) MDG_PCLK(41);
-        if (p == 3) MDG_PCLK(43);
-        const double* rg = ring + stage * kStageDoubles + tid;
+        if (p + 1 < np) asm volatile("cp.async.wait_group 1;" ::: "memory");  // all but the newest group: pair p is here
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const double* rg = ring + stage * kBulkRows * BS + tid;
         price[0] = rg[0]; price[1] = rg[BS]; cur[0] = rg[2 * BS]; cur[1] = rg[3 * BS];
         mep[0] = rg[4 * BS]; mep[1] = rg[5 * BS]; bm[0] = rg[6 * BS]; bm[1] = rg[7 * BS];
         mean = rg[8 * BS];
-        if (tma_units) {
-          const double2 u2 = *reinterpret_cast<const double2*>(ring + stage * kStageDoubles + kBulkRows * BS + 2 * tid);
-          units[0] = u2.x; units[1] = u2.y;
-        }
-        __syncthreads();  // every thread has taken its values: the stage is free for the pair after next
-        if (p == 0) MDG_PCLK(42);
-        if (p == 3) MDG_PCLK(44);
-        if (tid == 0 && p + kBulkStages < np) bulk_issue(p + kBulkStages, stage);
+        if (p + kBulkStages < np) stage_issue(p + kBulkStages, stage);  // own column: program order is enough
       } else {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -747,11 +699,9 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
           price[q] = S.price[o]; cur[q] = S.ledger[o]; mep[q] = S.mean_entry[o]; bm[q] = S.borrowed[o];
         }
       }
-      if (tma_units) {
-        // (taken from the ring above)
-      } else if (units_v2) {
-        const double2 u2 = __ldcg(reinterpret_cast<const double2*>(urow + 2 * p));
-        units[0] = u2.x; units[1] = u2.y;
+      if (units_v2) {
+        units[0] = u_next.x; units[1] = u_next.y;
+        if (p + 1 < np) u_next = __ldcg(reinterpret_cast<const double2*>(urow + 2 * (p + 1)));
       } else {
         units[0] = (mode == MDG_MODE_MULTI && !arow && !wrow) ? urow[2 * p] : 0.;
         units[1] = (mode == MDG_MODE_MULTI && !arow && !wrow) ? urow[2 * p + 1] : 0.;
@@ -767,14 +717,6 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
         mean = S.gstate[(int64_t)P.gen[2 * p].gslot * N + e];
         if (p + MDG_PFDIST < np) prefetch_hint(p + MDG_PFDIST);
       }
-#if defined(MDG_PHASE_CLOCKS) && defined(MDG_PCLK_USE)
-      {  // force the operands to have arrived before the clock is read: 1 = state values, 2 = units, 3 = both
-        double chk = 0.;
-        if (MDG_PCLK_USE & 1) chk += price[0] + cur[0] + mep[0] + bm[0] + price[1] + cur[1] + mep[1] + bm[1] + mean;
-        if (MDG_PCLK_USE & 2) chk += units[0] + units[1];
-        if (chk == 1.2345e300) __trap();
-      }
-#endif
       MDG_PCLK(3 + 4 * p);
       {
 #pragma unroll
@@ -1012,65 +954,6 @@ static inline int fill_groups(const MdgParams& P, int8_t* leader) {
   return n;
 }
 
-// ---- tensor maps of the TMA staging path (driver entry point through the runtime: no -lcuda) --------------
-typedef CUresult (*StepEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static inline StepEncodeTiledFn step_tensor_map_encoder() {
-  static const StepEncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return (StepEncodeTiledFn)p;
-  }();
-  return fn;
-}
-// Encoding a map costs about a microsecond of host time: a launch's maps depend only on (base, spacing, N, nA), which
-// repeat from step to step, so the last few are kept per host thread.
-struct StepMapKey {
-  const void* base;
-  int64_t spacing, N;
-  int nA, kind;
-  bool operator==(const StepMapKey& o) const {
-    return base == o.base && spacing == o.spacing && N == o.N && nA == o.nA && kind == o.kind;
-  }
-};
-static inline bool step_tensor_map(const StepMapKey& k, CUtensorMap* out) {
-  constexpr int kSlots = 32;
-  thread_local StepMapKey keys[kSlots];
-  thread_local CUtensorMap maps[kSlots];
-  thread_local int used = 0, next = 0;
-  for (int i = 0; i < used; ++i)
-    if (keys[i] == k) { *out = maps[i]; return true; }
-  StepEncodeTiledFn enc = step_tensor_map_encoder();
-  if (!enc) return false;
-  CUtensorMap m;
-  CUresult cr;
-  if (k.kind == 0) {  // state slab: N x nA x 4 tensors, box 128 x 2 x 4
-    const cuuint64_t gdim[3] = {(cuuint64_t)k.N, (cuuint64_t)k.nA, 4};
-    const cuuint64_t gstr[2] = {(cuuint64_t)k.N * sizeof(double), (cuuint64_t)k.spacing};
-    const cuuint32_t box[3] = {128, 2, 4}, estr[3] = {1, 1, 1};
-    cr = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(k.base), gdim, gstr, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {  // units (N, nA) env-major: nA x N, box 2 x 128
-    const cuuint64_t gdim[2] = {(cuuint64_t)k.nA, (cuuint64_t)k.N};
-    const cuuint64_t gstr[1] = {(cuuint64_t)k.nA * sizeof(double)};
-    const cuuint32_t box[2] = {2, 128}, estr[2] = {1, 1};
-    cr = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(k.base), gdim, gstr, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  }
-  if (cr != CUDA_SUCCESS) return false;
-  const int slot = used < kSlots ? used++ : (next = (next + 1) % kSlots);
-  keys[slot] = k;
-  maps[slot] = m;
-  *out = m;
-  return true;
-}
-
 static inline int launch_step(StepArgs& a) {
   const int64_t N = a.L.n_envs;
   cudaStream_t st = (cudaStream_t)a.L.stream;
@@ -1087,30 +970,11 @@ static inline int launch_step(StepArgs& a) {
   static const int bulk_off = [] { const char* v = getenv("MDG_NO_BULK"); return v ? atoi(v) : 0; }();
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool small = N <= 148 * 512 * 2;  // up to two waves at 4 blocks per SM
-  // Staging of the pairs' state through shared memory (see step_body).  bulk = 2 (TMA tensor copies: one 3-D box for
-  // the eight state rows, one 2-D box for the units, needs the four state tensors equally spaced): 37.2 us against
-  // 39.4 us at 65,536 envs per launch, 426 against 437 us at 1,048,576.  bulk = 1 (nine row copies, any layout):
-  // neutral in the one-wave variant, 4 % slower in the multi-wave one, so only used in the former.
-  a.bulk = (pairs && !bulk_off && N % 128 == 0 && al16(a.S.price) && al16(a.S.ledger) && al16(a.S.mean_entry) &&
-            al16(a.S.borrowed) && al16(a.S.gstate)) ? 1 : 0;
-  a.tma_units = 0;
-  static const int tma_off = [] { const char* v = getenv("MDG_NO_TMA"); return v ? atoi(v) : 0; }();
-  if (a.bulk && !tma_off) {
-    // the four state tensors as ONE 3-D tensor: they have to be equally spaced (Env allocates them as one slab)
-    const char *p0 = (const char*)a.S.price, *p1 = (const char*)a.S.ledger, *p2 = (const char*)a.S.mean_entry,
-               *p3 = (const char*)a.S.borrowed;
-    const int64_t sp = p1 - p0;
-    if (sp >= (int64_t)a.P.n_assets * N * 8 && (sp & 15) == 0 && p2 - p1 == sp && p3 - p2 == sp && N <= 0x7fffffff &&
-        step_tensor_map(StepMapKey{a.S.price, sp, N, a.P.n_assets, 0}, &a.tm_state)) {
-      a.bulk = 2;
-      const bool by_units = a.L.mode == MDG_MODE_MULTI && a.IO.units && !a.IO.actions && !a.IO.weights;
-      if (by_units && a.units_v2 && step_tensor_map(StepMapKey{a.IO.units, 0, N, a.P.n_assets, 1}, &a.tm_units))
-        a.tma_units = 1;
-    }
-  }
-  if (a.bulk == 1 && !small) a.bulk = 0;
+  // (bulk staging only in the one-wave variant: measured neutral there -- 39.3 us either way at 65,536 envs -- and
+  // 4 % slower in the multi-wave regime, where the per-pair block barrier couples the warps)
+  a.bulk = (pairs && small && !bulk_off) ? 1 : 0;
   const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128 +
-                      (a.bulk ? sizeof(double) * kBulkStages * kStageDoubles + 16 : 0);
+                      (a.bulk ? sizeof(double) * kBulkStages * kBulkRows * 128 : 0);
   if (smem > 48 * 1024) {  // the bulk ring lifts the all-pairs kernels above the default dynamic shared-memory limit
     static const cudaError_t attr = [] {
       cudaError_t e_ = cudaSuccess;
@@ -1119,7 +983,6 @@ static inline int launch_step(StepArgs& a) {
         if (r_ != cudaSuccess) e_ = r_;
       };
       set((const void*)step_kernel<true, 128, 4, true, true>); set((const void*)step_kernel<true, 128, 4, false, true>);
-      set((const void*)step_kernel<true, 128, 3, true, true>); set((const void*)step_kernel<true, 128, 3, false, true>);
       return e_;
     }();
     if (attr != cudaSuccess) return cuda_err(attr, "mdg_step shared-memory opt-in");
@@ -1129,9 +992,6 @@ static inline int launch_step(StepArgs& a) {
   if (small && a.bulk) {
     if (acts) step_kernel<true, 128, 4, true, true><<<grid, 128, smem, st>>>(a);
     else step_kernel<true, 128, 4, false, true><<<grid, 128, smem, st>>>(a);
-  } else if (a.bulk) {
-    if (acts) step_kernel<true, 128, 3, true, true><<<grid, 128, smem, st>>>(a);
-    else step_kernel<true, 128, 3, false, true><<<grid, 128, smem, st>>>(a);
   } else if (small) {
     if (pairs) { if (acts) MDG_LAUNCH(true, 4, true); else MDG_LAUNCH(true, 4, false); }
     else { if (acts) MDG_LAUNCH(false, 4, true); else MDG_LAUNCH(false, 4, false); }
