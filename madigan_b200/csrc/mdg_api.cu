@@ -598,6 +598,9 @@ extern "C" int mdg_refresh_folds(const MdgParams* P, const MdgState* S, const Md
 extern "C" int mdg_debug_phase_clocks(long long* out) {
   return cuda_err(cudaMemcpyFromSymbol(out, mdg::g_phase_clk, sizeof(long long) * 64 * 64), "phase clocks");
 }
+extern "C" int mdg_debug_block_times(unsigned long long* out) {
+  return cuda_err(cudaMemcpyFromSymbol(out, mdg::g_block_ns, sizeof(unsigned long long) * 1024 * 4), "block times");
+}
 #endif
 
 extern "C" int mdg_abi_version(void) { return MDG_ABI_VERSION; }

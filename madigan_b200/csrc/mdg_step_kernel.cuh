@@ -63,7 +63,7 @@ constexpr int kBlock = 128;
 constexpr int kRngUnroll = MDG_RNG_UNROLL, kTailUnroll = MDG_TAIL_UNROLL;  // #pragma unroll does not expand macros
 
 // ---- bulk-copy staging of the state rows (sm_90+: cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS)
-constexpr int kStageDoubles = 11 * 128;  // per stage and 128-thread block: nine rows + the pair's units (2 per env)
+constexpr int kStageRows = 11;  // per stage: nine rows of BS doubles + the pair's units (2 per env)
 constexpr int kBulkRows = 9;    // per pair: price x2, ledger x2, mean entry x2, borrowed margin x2, the pair's mean
 constexpr int kBulkStages = 2;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -531,6 +531,12 @@ __device__ __forceinline__ int gen_state_rows(const MdgAssetGen& g) {
 #define MDG_PCLK_TID 0
 #endif
 __device__ long long g_phase_clk[64 * 64];
+__device__ unsigned long long g_block_ns[1024 * 4];  // per block: %globaltimer at entry / exit of thread 0, %smid
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 #define MDG_PCLK(slot)                                                                                     \
   do {                                                                                                     \
     if (threadIdx.x == MDG_PCLK_TID && blockIdx.x < 64) g_phase_clk[blockIdx.x * 64 + (slot)] = clock64(); \
@@ -542,6 +548,14 @@ __device__ long long g_phase_clk[64 * 64];
 template <bool PAIRS, int BS, bool ACTIONS, bool TX2, bool BULK>
 __device__ __forceinline__ void step_body(const StepArgs& a) {
   MDG_PCLK(0);
+#ifdef MDG_PHASE_CLOCKS
+  if (threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    g_block_ns[blockIdx.x * 4] = global_ns();
+    g_block_ns[blockIdx.x * 4 + 2] = smid;
+  }
+#endif
   // per-thread stash, [2*nA][BS]: position value after the tick, and prev value + mar_diff (and, in the
   // all-pairs kernel, this step's normals before they are consumed; see stash_normal_row)
   extern __shared__ __align__(128) double stash[];
@@ -564,7 +578,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   // shared memory instead of L2 (the prefetch.global.L1 hints still left an L2 round trip on every first use).
   constexpr bool bulk = PAIRS && BULK;
   double* ring = stash + 2 * na * BS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kBulkStages * kStageDoubles);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kBulkStages * kStageRows * BS);
   const int64_t e0 = (int64_t)blockIdx.x * BS;
   const bool tma = bulk && a.bulk == 2;
   const bool tma_units = tma && a.tma_units;
@@ -572,7 +586,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   // 2-D tensor copy gathers the pair's 16 bytes of every env's units row (box 2 x 128), one bulk copy the mean row
   auto tma_issue = [&](int pp, int stage) {  // one thread
     const uint32_t mb = smem_u32(&full[stage]);
-    double* sb = ring + stage * kStageDoubles;
+    double* sb = ring + stage * kStageRows * BS;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb),
                  "r"((uint32_t)((kBulkRows + (tma_units ? 2 : 0)) * BS * sizeof(double)))
                  : "memory");
@@ -605,7 +619,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
 #pragma unroll
     for (int r = 0; r < kBulkRows; ++r)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_u32(ring + stage * kStageDoubles + r * BS)),
+                       smem_u32(ring + stage * kStageRows * BS + r * BS)),
                    "l"(src[r]), "r"((uint32_t)(BS * sizeof(double))), "r"(mb)
                    : "memory");
   };
@@ -728,12 +742,12 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
         mbar_wait(&full[stage], (uint32_t)((p >> 1) & 1));
         if (p == 0) MDG_PCLK(41);
         if (p == 3) MDG_PCLK(43);
-        const double* rg = ring + stage * kStageDoubles + tid;
+        const double* rg = ring + stage * kStageRows * BS + tid;
         price[0] = rg[0]; price[1] = rg[BS]; cur[0] = rg[2 * BS]; cur[1] = rg[3 * BS];
         mep[0] = rg[4 * BS]; mep[1] = rg[5 * BS]; bm[0] = rg[6 * BS]; bm[1] = rg[7 * BS];
         mean = rg[8 * BS];
         if (tma_units) {
-          const double2 u2 = *reinterpret_cast<const double2*>(ring + stage * kStageDoubles + kBulkRows * BS + 2 * tid);
+          const double2 u2 = *reinterpret_cast<const double2*>(ring + stage * kStageRows * BS + kBulkRows * BS + 2 * tid);
           units[0] = u2.x; units[1] = u2.y;
         }
         __syncthreads();  // every thread has taken its values: the stage is free for the pair after next
@@ -981,6 +995,9 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
     a.IO.n_popped[e] = n_popped;
   }
   MDG_PCLK(40);
+#ifdef MDG_PHASE_CLOCKS
+  if (threadIdx.x == 0 && blockIdx.x < 1024) g_block_ns[blockIdx.x * 4 + 1] = global_ns();
+#endif
 }
 
 template <bool PAIRS, int BS, int MINB, bool ACTIONS, bool BULK = false>
@@ -989,6 +1006,15 @@ __global__ void __launch_bounds__(BS, MINB) step_kernel(const __grid_constant__ 
 #define MDG_BULK_TX2 0
 #endif
   step_body<PAIRS, BS, ACTIONS, (MINB < 4) || (BULK && MDG_BULK_TX2), BULK>(a);  // MINB 3 = the multi-wave register budget
+}
+
+// 64-thread blocks, seven per SM (one-wave launches): at 128 registers (registers are granted per warp in units that make 136 or 144 x 14 warps overflow the file: measured two waves)
+#ifndef MDG_BS64_REGS
+#define MDG_BS64_REGS 128
+#endif
+template <bool ACTIONS, bool BULK>
+__global__ void __maxnreg__(MDG_BS64_REGS) step_kernel64(const __grid_constant__ StepArgs a) {
+  step_body<true, 64, ACTIONS, false, BULK>(a);
 }
 
 // host side: is every asset part of an OUPair laid out (role0, role1) with in-order noise slots?
@@ -1032,9 +1058,9 @@ static inline StepEncodeTiledFn step_tensor_map_encoder() {
 struct StepMapKey {
   const void* base;
   int64_t spacing, N;
-  int nA, kind;
+  int nA, kind, bs;
   bool operator==(const StepMapKey& o) const {
-    return base == o.base && spacing == o.spacing && N == o.N && nA == o.nA && kind == o.kind;
+    return base == o.base && spacing == o.spacing && N == o.N && nA == o.nA && kind == o.kind && bs == o.bs;
   }
 };
 static inline bool step_tensor_map(const StepMapKey& k, CUtensorMap* out) {
@@ -1051,14 +1077,14 @@ static inline bool step_tensor_map(const StepMapKey& k, CUtensorMap* out) {
   if (k.kind == 0) {  // state slab: N x nA x 4 tensors, box 128 x 2 x 4
     const cuuint64_t gdim[3] = {(cuuint64_t)k.N, (cuuint64_t)k.nA, 4};
     const cuuint64_t gstr[2] = {(cuuint64_t)k.N * sizeof(double), (cuuint64_t)k.spacing};
-    const cuuint32_t box[3] = {128, 2, 4}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)k.bs, 2, 4}, estr[3] = {1, 1, 1};
     cr = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(k.base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {  // units (N, nA) env-major: nA x N, box 2 x 128
     const cuuint64_t gdim[2] = {(cuuint64_t)k.nA, (cuuint64_t)k.N};
     const cuuint64_t gstr[1] = {(cuuint64_t)k.nA * sizeof(double)};
-    const cuuint32_t box[2] = {2, 128}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {2, (cuuint32_t)k.bs}, estr[2] = {1, 1};
     cr = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(k.base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1082,7 +1108,7 @@ static inline int launch_step(StepArgs& a) {
   a.c_g1 = 6. + 3. * fabs(a.P.slippage_rel) + fabs(a.P.tcost_rel);
   a.c_g2 = 3. * fabs(a.P.slippage_abs);
   a.c_force_exact = (a.L.flags & MDG_FLAG_FORCE_EXACT_GATE) ? 1 : 0;
-  const unsigned grid = (unsigned)((N + 127) / 128);
+
   a.units_v2 = (a.IO.units && (reinterpret_cast<uintptr_t>(a.IO.units) & 15) == 0 && a.P.n_assets % 2 == 0) ? 1 : 0;
   static const int bulk_off = [] { const char* v = getenv("MDG_NO_BULK"); return v ? atoi(v) : 0; }();
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -1091,7 +1117,14 @@ static inline int launch_step(StepArgs& a) {
   // the eight state rows, one 2-D box for the units, needs the four state tensors equally spaced): 37.2 us against
   // 39.4 us at 65,536 envs per launch, 426 against 437 us at 1,048,576.  bulk = 1 (nine row copies, any layout):
   // neutral in the one-wave variant, 4 % slower in the multi-wave one, so only used in the former.
-  a.bulk = (pairs && !bulk_off && N % 128 == 0 && al16(a.S.price) && al16(a.S.ledger) && al16(a.S.mean_entry) &&
+  // MDG_BS64=1 (profiling knob): one-wave launches with 64-thread blocks, seven per SM.  65,536 envs are 2,048 warps,
+  // 13.8 per SM; 128-thread blocks put 16 warps on 68 of the SMs and 12 on the rest, 64-thread blocks 14 on nearly all.
+  // Measured (profiles/block_times.py, r2_notes.md): the launch still ends with the youngest block of the fullest SMs
+  // at ~30.5 us either way; 36.2 against 37.1 us for a lone launch, no difference inside bench.py -- not the default.
+  static const int bs64_on = [] { const char* v = getenv("MDG_BS64"); return v ? atoi(v) : 0; }();
+  const int bs = (pairs && bs64_on && N <= 148 * 7 * 64) ? 64 : 128;
+  const unsigned grid = (unsigned)((N + bs - 1) / bs);
+  a.bulk = (pairs && !bulk_off && N % bs == 0 && al16(a.S.price) && al16(a.S.ledger) && al16(a.S.mean_entry) &&
             al16(a.S.borrowed) && al16(a.S.gstate)) ? 1 : 0;
   a.tma_units = 0;
   static const int tma_off = [] { const char* v = getenv("MDG_NO_TMA"); return v ? atoi(v) : 0; }();
@@ -1101,16 +1134,16 @@ static inline int launch_step(StepArgs& a) {
                *p3 = (const char*)a.S.borrowed;
     const int64_t sp = p1 - p0;
     if (sp >= (int64_t)a.P.n_assets * N * 8 && (sp & 15) == 0 && p2 - p1 == sp && p3 - p2 == sp && N <= 0x7fffffff &&
-        step_tensor_map(StepMapKey{a.S.price, sp, N, a.P.n_assets, 0}, &a.tm_state)) {
+        step_tensor_map(StepMapKey{a.S.price, sp, N, a.P.n_assets, 0, bs}, &a.tm_state)) {
       a.bulk = 2;
       const bool by_units = a.L.mode == MDG_MODE_MULTI && a.IO.units && !a.IO.actions && !a.IO.weights;
-      if (by_units && a.units_v2 && step_tensor_map(StepMapKey{a.IO.units, 0, N, a.P.n_assets, 1}, &a.tm_units))
+      if (by_units && a.units_v2 && step_tensor_map(StepMapKey{a.IO.units, 0, N, a.P.n_assets, 1, bs}, &a.tm_units))
         a.tma_units = 1;
     }
   }
   if (a.bulk == 1 && !small) a.bulk = 0;
-  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * 128 +
-                      (a.bulk ? sizeof(double) * kBulkStages * kStageDoubles + 16 : 0);
+  const size_t smem = sizeof(double) * 2 * (size_t)a.P.n_assets * bs +
+                      (a.bulk ? sizeof(double) * kBulkStages * kStageRows * bs + 16 : 0);
   if (smem > 48 * 1024) {  // the bulk ring lifts the all-pairs kernels above the default dynamic shared-memory limit
     static const cudaError_t attr = [] {
       cudaError_t e_ = cudaSuccess;
@@ -1126,7 +1159,15 @@ static inline int launch_step(StepArgs& a) {
   }
   const bool acts = a.L.mode == MDG_MODE_MULTI && (a.IO.actions || a.IO.weights);
 #define MDG_LAUNCH(PAIRS_, MINB_, ACT_) step_kernel<PAIRS_, 128, MINB_, ACT_><<<grid, 128, smem, st>>>(a)
-  if (small && a.bulk) {
+  if (bs == 64) {
+    if (a.bulk) {
+      if (acts) step_kernel64<true, true><<<grid, 64, smem, st>>>(a);
+      else step_kernel64<false, true><<<grid, 64, smem, st>>>(a);
+    } else {
+      if (acts) step_kernel64<true, false><<<grid, 64, smem, st>>>(a);
+      else step_kernel64<false, false><<<grid, 64, smem, st>>>(a);
+    }
+  } else if (small && a.bulk) {
     if (acts) step_kernel<true, 128, 4, true, true><<<grid, 128, smem, st>>>(a);
     else step_kernel<true, 128, 4, false, true><<<grid, 128, smem, st>>>(a);
   } else if (a.bulk) {
