@@ -530,6 +530,9 @@ __device__ __forceinline__ int gen_state_rows(const MdgAssetGen& g) {
 #ifndef MDG_PCLK_TID
 #define MDG_PCLK_TID 0
 #endif
+#ifndef MDG_PCLK_B0
+#define MDG_PCLK_B0 0  // first of the 64 blocks that record
+#endif
 __device__ long long g_phase_clk[64 * 64];
 __device__ unsigned long long g_block_ns[1024 * 4];  // per block: %globaltimer at entry / exit of thread 0, %smid
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -539,7 +542,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 #define MDG_PCLK(slot)                                                                                     \
   do {                                                                                                     \
-    if (threadIdx.x == MDG_PCLK_TID && blockIdx.x < 64) g_phase_clk[blockIdx.x * 64 + (slot)] = clock64(); \
+    if (threadIdx.x == MDG_PCLK_TID && blockIdx.x >= MDG_PCLK_B0 && blockIdx.x < MDG_PCLK_B0 + 64)         \
+      g_phase_clk[(blockIdx.x - MDG_PCLK_B0) * 64 + (slot)] = clock64();                                   \
   } while (0)
 #else
 #define MDG_PCLK(slot)
