@@ -653,6 +653,10 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   }
   // The reduced reward's n-step shaper with nstep == 1 (add, pop at once: the common case) runs inline in the tail;
   // its moments are loaded here, at the start, so that no load latency is left at the end of the thread's chain.
+  // The env's tick is the first thing requested: it is all the normals need, and they are generated below while the
+  // rest of the prologue's loads (and everybody else's: every block of a one-wave launch starts at the same moment,
+  // profiles/phase_clocks.py: the youngest block of an SM left the prologue 6,000 cycles after the oldest) arrive.
+  const int64_t ts = S.timestamp[e];
   const bool inline_shaper = shaping && a.R.reduce_rewards && a.R.shaper != MDG_SHAPER_COSINE && a.R.nstep == 1 &&
                              (moments || a.R.shaper == MDG_SHAPER_SUM);
   double shA = 0., shB = 0.;
@@ -666,7 +670,6 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
 
   StepAcc A;
   A.cash = S.cash[e];
-  const int64_t ts = S.timestamp[e];
   // Folds of the incoming portfolio.  They are exactly the folds this kernel (or reset/init/refresh)
   // computed at the end of the previous call -- same values, same left-to-right order -- so they are
   // carried in state instead of re-reading the whole portfolio before the first transaction.
@@ -688,6 +691,26 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
     __syncthreads();
     if (tid == 0) bulk_issue(0, 0);
   }
+  const uint32_t gid = (uint32_t)(a.L.env_offset + e);
+  const uint32_t k0 = (uint32_t)a.L.seed, k1 = (uint32_t)(a.L.seed >> 32);
+  const uint32_t t_lo = (uint32_t)(uint64_t)ts, t_hi = (uint32_t)((uint64_t)ts >> 32);
+  if (PAIRS) {
+    const int np = na >> 1;
+    // This step's normals, all at once: the Philox + Box-Muller blocks are independent of each other and of
+    // the ledger, so they are generated four at a time (four interleaved dependency chains per thread --
+    // the kernel is latency-bound at one thread per env) while the first loads are in flight.
+    if (!a.IO.normals) {
+      const int nslots = 3 * np, nblk = (nslots + 1) >> 1;
+#pragma unroll kRngUnroll
+      for (int b = 0; b < nblk; ++b) {
+        double za, zb;
+        normal_block(gid, (uint32_t)b, t_lo, t_hi, k0, k1, za, zb);
+        st[stash_normal_row(2 * b) * BS] = za;
+        if (2 * b + 1 < nslots) st[stash_normal_row(2 * b + 1) * BS] = zb;
+      }
+    }
+  }
+  MDG_PCLK(2);
   A.pav = A.pml = A.pbm = A.pse = A.nav = A.gsum = 0.;
   A.bad_risk = false;
   const double prevEq = A.cash + A.rAV - A.rBM;  // Env.h:190,208,234
@@ -711,30 +734,12 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   const StepConsts c{};  // (tag: the values live in the kernel parameters, StepArgs.c_*)
   A.G += na * fabs(P.tcost_abs);  // the absolute cost of up to nA transactions
 
-  const uint32_t gid = (uint32_t)(a.L.env_offset + e);
-  const uint32_t k0 = (uint32_t)a.L.seed, k1 = (uint32_t)(a.L.seed >> 32);
-  const uint32_t t_lo = (uint32_t)(uint64_t)ts, t_hi = (uint32_t)((uint64_t)ts >> 32);
-
   MDG_PCLK(1);
   if (PAIRS) {
     // ---- headline path: every asset belongs to an OU pair.  One iteration = one pair; the next pair's
     // state and units are loaded while the current pair is processed (software prefetch).
     const int np = na >> 1;
-    // This step's normals, all at once: the Philox + Box-Muller blocks are independent of each other and of
-    // the ledger, so they are generated four at a time (four interleaved dependency chains per thread --
-    // the kernel is latency-bound at one thread per env) while the first loads are in flight.
-    if (!a.IO.normals) {
-      const int nslots = 3 * np, nblk = (nslots + 1) >> 1;
-#pragma unroll kRngUnroll
-      for (int b = 0; b < nblk; ++b) {
-        double za, zb;
-        normal_block(gid, (uint32_t)b, t_lo, t_hi, k0, k1, za, zb);
-        st[stash_normal_row(2 * b) * BS] = za;
-        if (2 * b + 1 < nslots) st[stash_normal_row(2 * b + 1) * BS] = zb;
-      }
-    }
     if (bulk && tid == 0 && na > 2) bulk_issue(1, 1);
-    MDG_PCLK(2);
 #pragma unroll 1
     for (int p = 0; p < np; ++p) {
       double price[2], cur[2], mep[2], bm[2], units[2], prev_val[2], tp[2], tu[2], tc[2];
