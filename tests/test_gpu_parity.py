@@ -9,6 +9,8 @@ pre-generated transaction units.  The bar (BASELINE.json north_star):
   * values that pass through libm transcendentals (log rewards, sin prices, pow in
     DSR/DDR): relative 1e-9 (CUDA's and glibc's log/sin/pow differ in the last ulp).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -465,3 +467,20 @@ def test_multi_wave_kernel_variant_parity():
             env.reset(mask=torch.from_numpy(orc.done.copy()), fill_history=True, normals=nz, uniforms=uz)
             orc.reset(mask=orc.done.copy(), fill_ticks=8, normals=nz, uniforms=uz)
     assert len(seen) >= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("knob", ["MDG_NO_TMA", "MDG_NO_BULK", "MDG_BS64"])
+def test_step_kernel_fallback_variants_parity(knob):
+    """The all-pairs step kernel picks its operand path per launch: TMA tensor copies (state tensors equally spaced, the
+    layout Env allocates), nine row copies (any 16-byte aligned layout; MDG_NO_TMA=1 forces it), plain loads
+    (MDG_NO_BULK=1), and an optional 64-thread-block instantiation (MDG_BS64=1).  The knobs are read once per process,
+    so each variant runs the pairs8 / headline oracle comparisons in a child process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, **{knob: "1"})
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "(pairs8 and (cash_account or margin_costs)) or headline_shape or autoreset_single_call"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
