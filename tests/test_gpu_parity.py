@@ -250,6 +250,16 @@ def test_step_parity_margin_costs_slippage(case):
     assert n_done >= 0
 
 
+@pytest.mark.parametrize("case,N", [("pairs8", 384), ("oupair", 256), ("pairs8", 128)])
+def test_step_parity_whole_blocks_tma_path(case, N):
+    """Launches of whole 128-env blocks take the TMA-staged operand path of the all-pairs kernel (3-D tensor copy of the
+    state slab, 2-D tensor copy of the units, two-stage ring); the sizes above (257, 300) take the plain-load path.
+    One pair (a single ring stage), eight pairs, one block and three blocks; leverage, costs, slippage, resets."""
+    run_case(case, N=N, T=50, margins=(.1, .25), costs=(.02, 1.5, .001, .002), scale=400_000.)
+    run_case(case, N=N, T=20, reward=dict(reward_shaper_config={"reward_shaper": "DSR", "adaptation_rate": .001},
+                                         nstep_return=1, reduce_rewards=True))
+
+
 def test_risk_paths_are_exercised():
     env, orc, P = make_pair("oupair", 512, margins=(.1, .25), costs=(.001, 0., 0., 0.))
     orc.reset(fill_ticks=1, clear_nstep=False)
