@@ -17,7 +17,10 @@ from madigan_b200 import _lib
 
 dev = torch.device("cuda", 0)
 hold = len(sys.argv) > 1 and sys.argv[1] == "hold"
-n, slabs = 65536, 8
+n = 65536
+slabs = int(os.environ.get("PCLK_SLABS", "8"))      # 1: the slab's pages stay in the TLBs (and its state in L2)
+flush = int(os.environ.get("PCLK_FLUSH", "0"))      # 1: write 256 MB between launches (L2-cold, TLB mostly warm)
+scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
 envs = [bench.make_env(dev, s * n, n_envs=n) for s in range(slabs)]
 acts = bench.synth_actions(4, n, 1, device=dev)
 for i in range(40 * slabs):
@@ -28,6 +31,8 @@ L.mdg_debug_phase_clocks.argtypes = [C.c_void_p]
 rows = []
 for i in range(3 * slabs):
     env = envs[i % slabs]
+    if flush:
+        scratch.fill_(i & 255)
     env.step(acts[i % 4] * 0. if hold else acts[i % 4])
     torch.cuda.synchronize()
     buf = np.zeros((64, 64), np.int64)
@@ -35,7 +40,7 @@ for i in range(3 * slabs):
     rows.append(buf - buf[:, :1])
     env._reset_launch(env.t["done"], bench.WINDOW, True, None, None)
 r = np.median(np.concatenate(rows[slabs:]), axis=0)  # median over blocks and launches, cycles since entry
-print("mode", "hold" if hold else "multi")
+print("mode", "hold" if hold else "multi", "slabs", slabs, "flush", flush)
 if r[2] < r[1]:  # final kernel: the normals are generated before the prologue's loaded values are first used
     print(f"tick load + ring set-up + normals {r[2]:.0f}  rest of the prologue {r[1] - r[2]:.0f}  loop {r[39] - r[1]:.0f}  tail {r[40] - r[39]:.0f}  total {r[40]:.0f} cycles")
     r[2] = r[1]
