@@ -234,6 +234,19 @@ def ncu_traffic():
         return None
 
 
+def ncu_pipes():
+    """What the same committed capture says about the secondary ceilings (say so when the kernel is bound
+    by instruction issue / the fp64 pipe rather than by DRAM): per cent of peak; None when the sources have changed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+            d = json.load(f)
+        if d.get("kernel_source_hash") != kernel_source_hash():
+            return None
+        return {k: d[k] for k in ("issue_active_pct", "fp64_pipe_pct", "dram_throughput_pct", "duration_us") if k in d}
+    except Exception:
+        return None
+
+
 def pin_to_gpu_numa_node(local):
     """Bind this process to the host cores nearest to GPU `local` (NVML's CPU affinity), before any pinned buffer is
     allocated: first-touch then places the staging buffers on the GPU's NUMA node, and 8 ranks stop sharing one
@@ -512,7 +525,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(world, slabs, args.setup_steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": which,
+                         "traffic": ncu_traffic(), "ncu": ncu_pipes(), "peak_source": which,
                          "kernel": "mdg::step_kernel<PAIRS=true, 128 threads, 4 blocks/SM>",
                          "kernel_ms": kern_ms, "kernel_ms_single_launch": kern_ms_single,
                          "kernel_timing": f"CUDA events around {slabs} consecutive launches (one per slab) on one stream, / {slabs}",
