@@ -526,7 +526,7 @@ def run_ours(args):
             "config": config_dict(world, slabs, args.setup_steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "ncu": ncu_pipes(), "peak_source": which,
-                         "kernel": "mdg::step_kernel<PAIRS=true, 128 threads, 4 blocks/SM>",
+                         "kernel": "mdg::step_kernel<PAIRS=true, 128 threads, 4 blocks/SM, TMA-staged operands>",
                          "kernel_ms": kern_ms, "kernel_ms_single_launch": kern_ms_single,
                          "kernel_timing": f"CUDA events around {slabs} consecutive launches (one per slab) on one stream, / {slabs}",
                          "algorithmic_bytes_per_launch": B * ENVS_PER_GPU},
