@@ -154,7 +154,10 @@ typedef struct MdgReward {
   double discounts[MDG_MAX_NSTEP]; /* math.pow(discount, i), filled by the host exactly as nstep_buffer.py:330 */
 } MdgReward;
 
-/* persistent per-env state, all [rows][N] */
+/* persistent per-env state, all [rows][N].
+ * Layout hint: when price, ledger, mean_entry and borrowed are equally spaced (views of one [4][nA][N] slab, 16-byte
+ * aligned, N a multiple of 128) the all-OU-pairs step kernel fetches a pair's eight state rows with ONE 3-D TMA tensor
+ * copy and the caller's units with a 2-D one; any other placement is accepted and read with plain loads. */
 typedef struct MdgState {
   double *price;      /* [nA][N] currentPrices (== currentData for synthetic sources) */
   double *ledger;     /* [nA][N] Portfolio::ledger_          */
