@@ -41,9 +41,10 @@ SEED = 0x6d616469_67616e00 ^ 5
 # env starts an episode at the same tick and the random policy ruins ~3 % of them per step, in waves; the finished
 # share -- each a reset with a 64-tick history fill, ~half the cost of a step kernel at 3 % -- decays slowly as the
 # population mixes: 3.0 % after 64 steps, 1.4 % after 256, 0.7 % after 1,024, 0.4 % after 4,096 (profiles/r2_notes.md).
-# 2,048 steps per slab (~0.6 s) put the timed region into the long-run regime a training run spends its life in; the
+# 16,384 steps per slab (~4 s; 20 steps cost 31.2 / 28.4 / 27.5 us per step after 2,048 / 8,192 / 16,384 of them)
+# put the timed region into the long-run regime a training run spends its life in; the
 # line reports the share it saw (done_rate_last_step).
-SETUP_STEPS = 2048
+SETUP_STEPS = 16384
 
 
 def bytes_per_env_step(nA=N_ASSETS, G=8, R=2, ra=1, sh=1):
@@ -409,6 +410,8 @@ def run_ours(args):
     launches0 = sum(e.launches for e in envs)
     t_region0 = time.perf_counter()
     ms_all = timed_region(lambda i: step_slab(i, acts[i % len(acts)]))
+    # share of the envs that finished in each slab's last step of this region (the later regions use other action batches)
+    done_rate_value = float(sum(float(e_.t["done"].float().mean()) for e_ in envs) / len(envs))
     launches = (sum(e.launches for e in envs) - launches0) // R_
     ms_total = sorted(ms_all)[len(ms_all) // 2]
     t_region1 = time.perf_counter()
@@ -546,6 +549,7 @@ def run_ours(args):
         # share of the envs that finished (and were reset with a 64-tick history fill) in the last step: the random
         # policy ruins ~3 % of the envs per step early on and fewer once the survivors' equity has grown
         line["done_rate_last_step"] = es["n_done"] / max(es["n_envs"], 1)  # (not in config: both arms print the same config)
+        line["done_rate_value_region"] = done_rate_value
         if world == 1 and not args.no_cpu_baseline:
             # in a subprocess: the reference's code is never loaded into the process that holds the product library
             try:
